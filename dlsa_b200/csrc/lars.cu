@@ -1,0 +1,462 @@
+// K6 + K7: LARS / lasso path on the least-squares approximation, then RSS / dof / AIC / BIC and argmin.
+//
+// Reference replaced: lars_lsa (dlsa/lsa.py:90-212; updateR :12-32, backsolvet :8-9, delcol :35-71,
+// downdateR :74-80); intercept branch as in the R original (dlsa/R/dlsa_alasso_func.R:115-125, 243-245);
+// first-argmin selection of dlsa() (dlsa/dlsa.py:90-91).
+//
+// The path is sequential (each knot depends on the previous one), so K6 is ONE persistent CTA: the O(m a)
+// correlation update runs on all threads against the L2-resident scaled Sigma, the triangular solves on the
+// upper Cholesky factor R (packed rows, shared memory when it fits) run on warp 0 with shuffles.
+// K7 evaluates the quadratic form of every knot in parallel (one CTA per knot) and K7b picks the minima.
+#include "common.cuh"
+
+namespace dlsa {
+
+constexpr int kLarsThreads = 512;
+constexpr int kLarsMaxM = 1024;          // vectors live in shared memory
+constexpr int kLarsRSmemDoubles = 16384;  // packed R kept in shared memory up to m = 180 (128 KB)
+
+struct LarsShared {
+    double Cmax, A, gamhat, zmin, red[kLarsThreads / 32];
+    int n_act, n_join, k, drops_pending, any_drop, err;
+    int ired[kLarsThreads / 32];
+};
+
+__device__ __forceinline__ size_t rpk(int l, int i, int m) {  // packed upper-triangular rows, i >= l
+    return (size_t)l * m - (size_t)l * (l - 1) / 2 + (i - l);
+}
+
+__device__ double block_reduce(double v, bool is_max, double* red) {
+    for (int s = 16; s >= 1; s >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, v, s);
+        v = is_max ? fmax(v, o) : fmin(v, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = red[0];
+    for (int w = 1; w < kLarsThreads / 32; w++) r = is_max ? fmax(r, red[w]) : fmin(r, red[w]);
+    __syncthreads();
+    return r;
+}
+
+__device__ double block_sum(double v, double* red) {
+    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int w = 0; w < kLarsThreads / 32; w++) r += red[w];
+    __syncthreads();
+    return r;
+}
+
+// warp 0: solve R' r = x in place (R upper, packed rows).  Column-oriented: row l of R is contiguous.
+__device__ void forward_solve_w0(const double* R, int a, int m, double* x) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        for (int l = 0; l < a; l++) {
+            const double rl = x[l] / R[rpk(l, l, m)];
+            __syncwarp();
+            if (lane == 0) x[l] = rl;
+            for (int i = l + 1 + lane; i < a; i += 32) x[i] = fma(-R[rpk(l, i, m)], rl, x[i]);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+// warp 0: solve R z = x in place (row-oriented dot products)
+__device__ void backward_solve_w0(const double* R, int a, int m, double* x) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        for (int l = a - 1; l >= 0; l--) {
+            double d = 0.0;
+            for (int i = l + 1 + lane; i < a; i += 32) d = fma(R[rpk(l, i, m)], x[i], d);
+            for (int s = 16; s >= 1; s >>= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
+            __syncwarp();
+            if (lane == 0) x[l] = (x[l] - d) / R[rpk(l, l, m)];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+// warp 0: delete column kdel of R (a x a) and restore triangularity with Givens rotations (dlsa/lsa.py:35-71)
+__device__ void delete_column_w0(double* R, int a, int m, int kdel) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        // rows l <= kdel: shift columns kdel+1.. left by one
+        for (int l = 0; l <= kdel; l++) {
+            for (int j0 = kdel; j0 < a - 1; j0 += 32) {
+                const int j = j0 + lane;
+                double v = 0.0;
+                if (j < a - 1) v = R[rpk(l, j + 1, m)];
+                __syncwarp();
+                if (j < a - 1 && j >= l) R[rpk(l, j, m)] = v;
+                __syncwarp();
+            }
+        }
+        for (int i = kdel + 1; i < a; i++) {
+            const double bb = R[rpk(i, i, m)];  // becomes the sub-diagonal entry (i, i-1) after the shift
+            __syncwarp();
+            for (int j0 = i; j0 < a - 1; j0 += 32) {  // shift row i left by one
+                const int j = j0 + lane;
+                double v = 0.0;
+                if (j < a - 1) v = R[rpk(i, j + 1, m)];
+                __syncwarp();
+                if (j < a - 1) R[rpk(i, j, m)] = v;
+                __syncwarp();
+            }
+            const double aa = R[rpk(i - 1, i - 1, m)];
+            double c = 1.0, s = 0.0;
+            if (bb != 0.0) {
+                if (!(fabs(bb) > fabs(aa))) {
+                    const double tau = -bb / aa;
+                    c = 1.0 / sqrt(1.0 + tau * tau);
+                    s = c * tau;
+                } else {
+                    const double tau = -aa / bb;
+                    s = 1.0 / sqrt(1.0 + tau * tau);
+                    c = s * tau;
+                }
+                __syncwarp();
+                if (lane == 0) R[rpk(i - 1, i - 1, m)] = c * aa - s * bb;
+                for (int j = i + lane; j < a - 1; j += 32) {
+                    const double x1 = R[rpk(i - 1, j, m)], x2 = R[rpk(i, j, m)];
+                    R[rpk(i - 1, j, m)] = c * x1 - s * x2;
+                    R[rpk(i, j, m)] = s * x1 + c * x2;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+struct LarsArgs {
+    const double* Sigma0;
+    const double* b0;
+    int p0, intercept, type, max_steps;
+    double n, eps;
+    double* beta_path;   // [(max_steps+1)][m]  (unscaled during the path; scaled by |b| in K7)
+    double* beta0_path;  // [(max_steps+1)]
+    double *rss, *aic, *bic;
+    int* dof;
+    int* info;
+    double* Sig;   // workspace [m*m] scaled Sigma
+    double* Rg;    // workspace packed R when it does not fit in shared memory
+    double* scal;  // workspace [4]: a11, beta0_init, (unused)
+};
+
+__global__ void __launch_bounds__(kLarsThreads, 1) lars_path_kernel(const LarsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ LarsShared sh;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int p0 = a.p0, off = a.intercept ? 1 : 0, m = p0 - off;
+    const double eps = a.eps;
+
+    double* Cvec = reinterpret_cast<double*>(smem_raw);
+    double* u = Cvec + m;       // Sig[:, act] w
+    double* w = u + m;          // direction over active (ordered like act)
+    double* Sign = w + m;
+    double* tmp = Sign + m;     // triangular-solve scratch
+    double* sgn = tmp + m;      // sign(b)
+    double* absb = sgn + m;
+    int* act = reinterpret_cast<int*>(absb + m);
+    int* state = act + m;       // 0 inactive, 1 active, 2 ignored
+    int* joiners = state + m;
+    unsigned char* dropflag = reinterpret_cast<unsigned char*>(joiners + m);
+    double* Rs = reinterpret_cast<double*>(smem_raw + ((size_t)(7 * m) * 8 + (size_t)(3 * m) * 4 + m + 15) / 16 * 16);
+    const bool r_in_smem = (size_t)m * (m + 1) / 2 <= kLarsRSmemDoubles;
+    double* R = r_in_smem ? Rs : a.Rg;
+
+    // ---- set-up: intercept profiling, adaptive rescaling (dlsa/lsa.py:98-109; R :115-131) ----------
+    const double a11 = a.intercept ? a.Sigma0[0] : 1.0;
+    for (int i = tid; i < m; i += nt) {
+        const double bi = a.b0[i + off];
+        absb[i] = fabs(bi);
+        sgn[i] = (bi > 0.0) ? 1.0 : ((bi < 0.0) ? -1.0 : 0.0);
+        state[i] = 0;
+    }
+    __syncthreads();
+    for (int e = tid; e < m * m; e += nt) {
+        const int i = e / m, j = e - i * m;
+        double v = a.Sigma0[(size_t)(i + off) * p0 + (j + off)];
+        if (a.intercept) v -= a.Sigma0[(size_t)(i + 1) * p0] * a.Sigma0[(size_t)(j + 1) * p0] / a11;
+        a.Sig[e] = absb[i] * v * absb[j];
+    }
+    if (a.intercept) {
+        double part = 0.0;
+        for (int i = tid; i < m; i += nt) part = fma(a.Sigma0[(size_t)(i + 1) * p0], a.b0[i + 1], part);
+        const double tot = block_sum(part, sh.red);
+        if (tid == 0) { a.scal[0] = a11; a.scal[1] = tot / a11; }
+    } else if (tid == 0) {
+        a.scal[0] = 1.0; a.scal[1] = 0.0;
+    }
+    __syncthreads();
+    for (int j = tid; j < m; j += nt) {
+        double c = 0.0;
+        for (int i = 0; i < m; i++) c = fma(sgn[i], a.Sig[(size_t)i * m + j], c);
+        Cvec[j] = c;
+        a.beta_path[j] = 0.0;
+    }
+    if (tid == 0) { sh.n_act = 0; sh.k = 0; sh.drops_pending = 0; sh.err = 0; }
+    __syncthreads();
+
+    const int max_steps = a.max_steps;
+    while (true) {
+        if (!(sh.k < max_steps && sh.n_act < m)) break;
+        __syncthreads();
+        if (tid == 0) sh.k += 1;
+        __syncthreads();
+        const int k = sh.k;
+        // Cmax over the inactive set (dlsa/lsa.py:128-129)
+        double cm = 0.0;
+        bool any_inactive = false;
+        for (int j = tid; j < m; j += nt)
+            if (state[j] == 0) { cm = fmax(cm, fabs(Cvec[j])); any_inactive = true; }
+        const double Cmax = block_reduce(cm, true, sh.red);
+        (void)any_inactive;
+        if (!sh.drops_pending) {
+            // joiners in ascending index order (:131-133)
+            if (tid == 0) {
+                int nj = 0;
+                for (int j = 0; j < m; j++)
+                    if (state[j] == 0 && fabs(Cvec[j]) >= Cmax - eps) joiners[nj++] = j;
+                sh.n_join = nj;
+            }
+            __syncthreads();
+            for (int jn = 0; jn < sh.n_join; jn++) {
+                const int inew = joiners[jn];
+                const int na = sh.n_act;
+                const double xnew = a.Sig[(size_t)inew * m + inew];
+                const double nx = sqrt(xnew);
+                if (na == 0) {
+                    if (tid == 0) {
+                        R[0] = nx;
+                        act[0] = inew; state[inew] = 1;
+                        Sign[0] = (Cvec[inew] > 0.0) ? 1.0 : ((Cvec[inew] < 0.0) ? -1.0 : 0.0);
+                        sh.n_act = 1;
+                    }
+                    __syncthreads();
+                    continue;
+                }
+                for (int l = tid; l < na; l += nt) tmp[l] = a.Sig[(size_t)inew * m + act[l]];
+                __syncthreads();
+                forward_solve_w0(R, na, m, tmp);  // updateR: r = backsolvet(R, xold)  (:19)
+                double part = 0.0;
+                for (int l = tid; l < na; l += nt) part = fma(tmp[l], tmp[l], part);
+                const double ss = block_sum(part, sh.red);
+                double rpp = nx * nx - ss;  // (:20)
+                if (rpp <= eps) {
+                    // machine-singular: back out and ignore the variable (:138-143; R :168-173)
+                    if (tid == 0) state[inew] = 2;
+                } else {
+                    rpp = sqrt(rpp);
+                    for (int l = tid; l < na; l += nt) R[rpk(l, na, m)] = tmp[l];
+                    if (tid == 0) {
+                        R[rpk(na, na, m)] = rpp;
+                        act[na] = inew; state[inew] = 1;
+                        Sign[na] = (Cvec[inew] > 0.0) ? 1.0 : ((Cvec[inew] < 0.0) ? -1.0 : 0.0);
+                        sh.n_act = na + 1;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        const int na = sh.n_act;
+        if (na == 0) {  // nothing could join (all remaining variables singular): stop
+            if (tid == 0) { sh.k -= 1; sh.err = 1; }
+            __syncthreads();
+            break;
+        }
+        // equiangular direction: Gi1 = R^-1 R^-T Sign, A = 1/sqrt(Gi1.Sign), w = A Gi1 (:151-153)
+        for (int l = tid; l < na; l += nt) tmp[l] = Sign[l];
+        __syncthreads();
+        forward_solve_w0(R, na, m, tmp);
+        backward_solve_w0(R, na, m, tmp);
+        double part = 0.0;
+        for (int l = tid; l < na; l += nt) part = fma(tmp[l], Sign[l], part);
+        const double gs = block_sum(part, sh.red);
+        const double A = 1.0 / sqrt(gs);
+        for (int l = tid; l < na; l += nt) w[l] = A * tmp[l];
+        __syncthreads();
+        // u_j = sum_l w_l Sig[act_l][j]  (serves both `a` (:157-160) and the Cvec update (:177))
+        for (int j = tid; j < m; j += nt) {
+            double s = 0.0;
+            for (int l = 0; l < na; l++) s = fma(w[l], a.Sig[(size_t)act[l] * m + j], s);
+            u[j] = s;
+        }
+        __syncthreads();
+        double gam = INFINITY;
+        if (na < m) {
+            for (int j = tid; j < m; j += nt) {
+                if (state[j] == 0) {
+                    const double cj = Cvec[j], aj = u[j];
+                    const double g1 = (Cmax - cj) / (A - aj), g2 = (Cmax + cj) / (A + aj);
+                    if (g1 > eps) gam = fmin(gam, g1);
+                    if (g2 > eps) gam = fmin(gam, g2);
+                }
+            }
+        }
+        double gamhat = block_reduce(gam, false, sh.red);
+        gamhat = fmin(gamhat, Cmax / A);  // (:155,162)
+        const double* bprev = a.beta_path + (size_t)(k - 1) * m;
+        double* bcur = a.beta_path + (size_t)k * m;
+        bool drop_now = false;
+        if (a.type == DLSA_LARS_LASSO) {  // (:164-173)
+            double zm = INFINITY;
+            for (int l = tid; l < na; l += nt) {
+                const double z1 = -bprev[act[l]] / w[l];
+                if (z1 > eps) zm = fmin(zm, z1);
+            }
+            double zmin = block_reduce(zm, false, sh.red);
+            zmin = fmin(zmin, gamhat);
+            if (zmin < gamhat) {
+                gamhat = zmin;
+                drop_now = true;
+                for (int l = tid; l < na; l += nt) dropflag[l] = ((-bprev[act[l]] / w[l]) == zmin) ? 1 : 0;
+            }
+        }
+        for (int j = tid; j < m; j += nt) {
+            bcur[j] = bprev[j];
+            Cvec[j] = fma(-gamhat, u[j], Cvec[j]);
+        }
+        __syncthreads();
+        for (int l = tid; l < na; l += nt) bcur[act[l]] += gamhat * w[l];
+        __syncthreads();
+        if (drop_now) {  // (:179-186)
+            for (int l = na - 1; l >= 0; l--) {
+                if (dropflag[l]) {
+                    delete_column_w0(R, sh.n_act, m, l);
+                    if (tid == 0) {
+                        const int na2 = sh.n_act;
+                        const int v = act[l];
+                        bcur[v] = 0.0;
+                        state[v] = 0;
+                        for (int t = l; t < na2 - 1; t++) { act[t] = act[t + 1]; Sign[t] = Sign[t + 1]; }
+                        sh.n_act = na2 - 1;
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        if (tid == 0) sh.drops_pending = drop_now ? 1 : 0;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        a.info[0] = sh.k + 1;
+        a.info[3] = sh.err;
+    }
+}
+
+// K7: one CTA per knot: RSS_k = (s - beta_k)' Sig (s - beta_k) (:191-192); scale beta by |b| (:198-201);
+// beta0 (R :243-245); dof (:208); AIC/BIC (:209-210).
+__global__ void __launch_bounds__(256) lars_ic_kernel(const LarsArgs a) {
+    __shared__ double red[8];
+    const int row = blockIdx.x;
+    if (row >= a.info[0]) return;
+    const int off = a.intercept ? 1 : 0, m = a.p0 - off;
+    extern __shared__ double d_s[];  // [m] s - beta
+    double* brow = a.beta_path + (size_t)row * m;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const double bj = a.b0[j + off];
+        const double sg = (bj > 0.0) ? 1.0 : ((bj < 0.0) ? -1.0 : 0.0);
+        d_s[j] = sg - brow[j];
+    }
+    __syncthreads();
+    double part = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        double s = 0.0;
+        const double* srow = a.Sig + (size_t)i * m;
+        for (int j = 0; j < m; j++) s = fma(srow[j], d_s[j], s);
+        part = fma(d_s[i], s, part);
+    }
+    for (int s = 16; s >= 1; s >>= 1) part += __shfl_xor_sync(0xffffffffu, part, s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    // scale, dof, beta0
+    double b0part = 0.0;
+    int dofpart = 0;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const double v = brow[j] * fabs(a.b0[j + off]);
+        brow[j] = v;
+        if (fabs(v) > a.eps) dofpart++;
+        if (a.intercept) b0part = fma(a.Sigma0[(size_t)(j + 1) * a.p0], v, b0part);
+    }
+    __shared__ double red2[8];
+    __shared__ int red3[8];
+    for (int s = 16; s >= 1; s >>= 1) {
+        b0part += __shfl_xor_sync(0xffffffffu, b0part, s);
+        dofpart += __shfl_xor_sync(0xffffffffu, dofpart, s);
+    }
+    if ((threadIdx.x & 31) == 0) { red2[threadIdx.x >> 5] = b0part; red3[threadIdx.x >> 5] = dofpart; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double rss = 0.0, bb = 0.0;
+        int dof = 0;
+        for (int w_ = 0; w_ < 8; w_++) { rss += red[w_]; bb += red2[w_]; dof += red3[w_]; }
+        a.rss[row] = rss;
+        a.dof[row] = dof;
+        a.bic[row] = rss + log(a.n) * (double)dof;
+        a.aic[row] = rss + 2.0 * (double)dof;
+        a.beta0_path[row] = a.intercept ? (a.scal[1] - bb / a.scal[0]) : 0.0;
+    }
+}
+
+// K7b: first-argmin of AIC and BIC (np.argmin, dlsa/dlsa.py:90-91)
+__global__ void lars_select_kernel(const LarsArgs a) {
+    if (threadIdx.x == 0) {
+        const int n = a.info[0];
+        int ia = 0, ib = 0;
+        for (int r = 1; r < n; r++) {
+            if (a.aic[r] < a.aic[ia]) ia = r;
+            if (a.bic[r] < a.bic[ib]) ib = r;
+        }
+        a.info[1] = ia;
+        a.info[2] = ib;
+    }
+}
+
+static size_t lars_vec_bytes(int m) { return ((size_t)(7 * m) * 8 + (size_t)(3 * m) * 4 + m + 15) / 16 * 16; }
+
+size_t lars_workspace_bytes(int p0, int max_steps) {
+    (void)max_steps;
+    const size_t m = (size_t)p0;
+    return (m * m + m * (m + 1) / 2 + 8) * sizeof(double);
+}
+
+int lars_launch(const double* Sigma0, const double* b0, int p0, int intercept, double n, int type, double eps,
+                int max_steps, double* beta_path, double* beta0_path, double* rss, double* aic, double* bic, int* dof,
+                int* info, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const int m = p0 - (intercept ? 1 : 0);
+    DLSA_REQUIRE(m >= 1 && m <= kLarsMaxM, DLSA_E_UNSUPPORTED, "lars: m=%d outside [1,%d]", m, kLarsMaxM);
+    DLSA_REQUIRE(workspace != nullptr && workspace_bytes >= lars_workspace_bytes(p0, max_steps), DLSA_E_WORKSPACE,
+                 "lars: workspace too small");
+    LarsArgs a;
+    a.Sigma0 = Sigma0; a.b0 = b0; a.p0 = p0; a.intercept = intercept ? 1 : 0; a.type = type;
+    a.max_steps = max_steps > 0 ? max_steps : 8 * m;
+    a.n = n; a.eps = eps;
+    a.beta_path = beta_path; a.beta0_path = beta0_path; a.rss = rss; a.aic = aic; a.bic = bic; a.dof = dof; a.info = info;
+    double* ws = static_cast<double*>(workspace);
+    a.scal = ws;
+    a.Sig = ws + 8;
+    a.Rg = a.Sig + (size_t)p0 * p0;
+    const bool r_in_smem = (size_t)m * (m + 1) / 2 <= kLarsRSmemDoubles;
+    const size_t smem = lars_vec_bytes(m) + (r_in_smem ? (size_t)m * (m + 1) / 2 * 8 : 0);
+    DLSA_CUDA(cudaFuncSetAttribute(lars_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lars_path_kernel<<<1, kLarsThreads, smem, st>>>(a);
+    count_launch();
+    int rc = check_launch("lars_path_kernel");
+    if (rc) return rc;
+    lars_ic_kernel<<<a.max_steps + 1, 256, (size_t)m * 8, st>>>(a);
+    count_launch();
+    rc = check_launch("lars_ic_kernel");
+    if (rc) return rc;
+    lars_select_kernel<<<1, 32, 0, st>>>(a);
+    count_launch();
+    return check_launch("lars_select_kernel");
+}
+
+}  // namespace dlsa

@@ -1,0 +1,302 @@
+"""Tensor-level engine: drives the C ABI (include/dlsa_b200.h) with PyTorch-owned device buffers.
+
+PyTorch is plumbing here (device memory, streams, torch.distributed); every number is produced by the
+hand-written sm_100a kernels in libdlsa_b200.so.  One process per GPU; partitions are sharded across
+ranks and the only cross-rank step is one allreduce of the packed sufficient statistic (combine_partitions).
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+_F64 = torch.float64
+
+
+@dataclasses.dataclass
+class EngineConfig:
+    """Solver settings.  Defaults follow the exact-Newton specification of dlsa/R/wlse_func.R:24-65 with the
+    oracle tolerance: start at 0, damp delta*0.01 when max|delta|>5, stop on max|delta|<=tol."""
+    tol: float = 1e-10
+    max_iter: int = 50
+    damp_above: float = 5.0
+    damp_factor: float = 0.01
+    want_loglik: bool = True
+
+
+@dataclasses.dataclass
+class PartitionFits:
+    """Per-partition map output: the tensor form of the p x (3+p) frames of dlsa/models.py:136-142."""
+    coef: torch.Tensor          # [K, p]
+    Sig_inv: torch.Tensor       # [K, p, p]
+    Sig_invMcoef: torch.Tensor  # [K, p]
+    status: torch.Tensor        # [K] int32, _lib.ST_*
+    iters: torch.Tensor         # [K] int32
+    loglik: Optional[torch.Tensor]  # [K] at the returned coef (None if not requested)
+    passes: int                 # fused passes launched (Newton iterations + the final Sig_inv pass)
+    n_rows: int
+
+
+@dataclasses.dataclass
+class CombineResult:
+    """dlsa_mapred output (dlsa/dlsa.py:55-59) in tensor form."""
+    beta_byOLS: torch.Tensor      # [p]
+    beta_byONESHOT: torch.Tensor  # [p]
+    Sig_inv_sum: torch.Tensor     # [p, p]
+    K_eff: int
+    K_total: int
+
+
+@dataclasses.dataclass
+class LarsResult:
+    """lars_lsa output (dlsa/lsa.py:211): AIC, BIC, beta, beta0 (+ RSS, dof, argmins)."""
+    AIC: torch.Tensor
+    BIC: torch.Tensor
+    beta: torch.Tensor
+    beta0: torch.Tensor
+    RSS: torch.Tensor
+    dof: torch.Tensor
+    argmin_AIC: int
+    argmin_BIC: int
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts: torch.Tensor) -> torch.device:
+    dev = ts[0].device
+    for t in ts:
+        if t.device.type != "cuda":
+            raise ValueError("dlsa_b200 runs on CUDA tensors only (there is no CPU path)")
+        if t.device != dev:
+            raise ValueError("all tensors must live on the same device")
+    return dev
+
+
+def _workspace(nbytes: int, dev) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=dev)
+
+
+def _check_inputs(X, y, part_offsets):
+    dev = _require_cuda(X, y, part_offsets)
+    if X.dtype != _F64 or y.dtype != _F64:
+        raise TypeError("X and y must be float64 (the reference's arithmetic type)")
+    if X.dim() != 2 or X.stride(1) != 1:
+        raise ValueError("X must be [n, p] row-major (stride(1) == 1)")
+    if part_offsets.dtype != torch.int64 or part_offsets.dim() != 1 or part_offsets.numel() < 1:
+        raise TypeError("part_offsets must be int64 [K+1]")
+    y = y.contiguous().view(-1)
+    if y.numel() != X.shape[0]:
+        raise ValueError("y and X disagree on the number of rows")
+    return dev, y
+
+
+def irls_pass(X, y, part_offsets, beta, fit_intercept=False, family=_lib.FAMILY_LOGISTIC, active=None,
+              max_part_rows=None, want_loglik=True, out=None, workspace=None):
+    """One fused pass (K1) over all partitions: returns (g[K,p], H[K,p,p], loglik[K] or None)."""
+    dev, y = _check_inputs(X, y, part_offsets)
+    K = part_offsets.numel() - 1
+    px = X.shape[1]
+    p = px + (1 if fit_intercept else 0)
+    if max_part_rows is None:
+        max_part_rows = int((part_offsets[1:] - part_offsets[:-1]).max().item()) if K > 0 else 0
+    if out is None:
+        g = torch.zeros(K, p, dtype=_F64, device=dev)
+        H = torch.zeros(K, p, p, dtype=_F64, device=dev)
+        ll = torch.zeros(K, dtype=_F64, device=dev) if want_loglik else None
+    else:
+        g, H, ll = out
+    need = lib.dlsa_irls_pass_workspace_bytes(K, p, max_part_rows)
+    if workspace is None or workspace.numel() < need:
+        workspace = _workspace(need, dev)
+    check(lib.dlsa_irls_pass_f64(X.data_ptr(), X.stride(0), y.data_ptr(), part_offsets.data_ptr(), K, px,
+                                 int(fit_intercept), family, _ptr(beta), _ptr(active), g.data_ptr(), H.data_ptr(),
+                                 _ptr(ll), max_part_rows, workspace.data_ptr(), workspace.numel(), _stream()),
+          "dlsa_irls_pass_f64")
+    return g, H, ll
+
+
+def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor, fit_intercept: bool = False,
+                            config: Optional[EngineConfig] = None, beta_init: Optional[torch.Tensor] = None
+                            ) -> PartitionFits:
+    """Per-partition logistic MLE for every partition at once (the map side, dlsa/models.py:42-147).
+
+    X [n, px] float64 row-major on the GPU with each partition's rows contiguous; ``part_offsets`` int64 [K+1].
+    Newton iterations = K1 (fused pass) + K2 (batched Cholesky update) until every partition has
+    max|delta| <= tol; one more K1 at the returned coefficients gives Sig_inv (dlsa/models.py:114,130),
+    then K3 gives Sig_invMcoef (:131).  With an intercept it is coefficient 0 (:116-122).
+    """
+    cfg = config or EngineConfig()
+    dev, y = _check_inputs(X, y, part_offsets)
+    K = part_offsets.numel() - 1
+    px = X.shape[1]
+    p = px + (1 if fit_intercept else 0)
+    sizes = part_offsets[1:] - part_offsets[:-1]
+    max_rows = int(sizes.max().item()) if K > 0 else 0
+    beta = torch.zeros(K, p, dtype=_F64, device=dev) if beta_init is None else beta_init.to(dev, _F64).clone()
+    g = torch.zeros(K, p, dtype=_F64, device=dev)
+    H = torch.zeros(K, p, p, dtype=_F64, device=dev)
+    ll = torch.zeros(K, dtype=_F64, device=dev)
+    status = torch.full((K,), _lib.ST_NOT_CONVERGED, dtype=torch.int32, device=dev)
+    active = torch.ones(K, dtype=torch.int32, device=dev)
+    iters = torch.zeros(K, dtype=torch.int32, device=dev)
+    n_active = torch.zeros(1, dtype=torch.int32, device=dev)
+    max_delta = torch.zeros(K, dtype=_F64, device=dev)
+    ws_pass = _workspace(lib.dlsa_irls_pass_workspace_bytes(K, p, max_rows), dev)
+    ws_chol = _workspace(lib.dlsa_newton_update_workspace_bytes(K, p), dev)
+    passes = 0
+    for _ in range(cfg.max_iter):
+        irls_pass(X, y, part_offsets, beta, fit_intercept, _lib.FAMILY_LOGISTIC, active, max_rows,
+                  want_loglik=False, out=(g, H, None), workspace=ws_pass)
+        passes += 1
+        n_active.zero_()
+        check(lib.dlsa_newton_update_f64(H.data_ptr(), g.data_ptr(), K, p, beta.data_ptr(), max_delta.data_ptr(),
+                                         status.data_ptr(), active.data_ptr(), iters.data_ptr(), n_active.data_ptr(),
+                                         cfg.tol, cfg.damp_above, cfg.damp_factor, ws_chol.data_ptr(),
+                                         ws_chol.numel(), _stream()), "dlsa_newton_update_f64")
+        if int(n_active.item()) == 0:  # the one host read per iteration
+            break
+    # final pass at the returned coefficients: Sig_inv (and the log-likelihood) for every partition
+    irls_pass(X, y, part_offsets, beta, fit_intercept, _lib.FAMILY_LOGISTIC, None, max_rows,
+              want_loglik=cfg.want_loglik, out=(g, H, ll if cfg.want_loglik else None), workspace=ws_pass)
+    passes += 1
+    Hb = torch.empty(K, p, dtype=_F64, device=dev)
+    check(lib.dlsa_batched_symv_f64(H.data_ptr(), beta.data_ptr(), K, p, Hb.data_ptr(), _stream()),
+          "dlsa_batched_symv_f64")
+    return PartitionFits(coef=beta, Sig_inv=H, Sig_invMcoef=Hb, status=status, iters=iters,
+                         loglik=ll if cfg.want_loglik else None, passes=passes, n_rows=int(X.shape[0]))
+
+
+def fit_linear_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor) -> PartitionFits:
+    """Per-partition OLS in closed form (R ``lm(y~x-1)`` + ``solve(vcov)``, dlsa/R/wlse_func.R:169-182):
+    one fused pass gives X'X, X'y, y'y (K8); theta_k by batched Cholesky; Sig_inv_k = X'X / sigma2_k."""
+    dev, y = _check_inputs(X, y, part_offsets)
+    K = part_offsets.numel() - 1
+    p = X.shape[1]
+    sizes = part_offsets[1:] - part_offsets[:-1]
+    max_rows = int(sizes.max().item()) if K > 0 else 0
+    g, H, yty = irls_pass(X, y, part_offsets, None, False, _lib.FAMILY_LINEAR, None, max_rows, want_loglik=True)
+    theta = torch.empty(K, p, dtype=_F64, device=dev)
+    status = torch.zeros(K, dtype=torch.int32, device=dev)
+    ws = _workspace(lib.dlsa_newton_update_workspace_bytes(K, p), dev)
+    check(lib.dlsa_spd_solve_f64(H.data_ptr(), g.data_ptr(), K, p, theta.data_ptr(), status.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), _stream()), "dlsa_spd_solve_f64")
+    sigma2 = torch.empty(K, dtype=_F64, device=dev)
+    check(lib.dlsa_ols_scale_f64(H.data_ptr(), g.data_ptr(), yty.data_ptr(), theta.data_ptr(),
+                                 part_offsets.data_ptr(), K, p, sigma2.data_ptr(), _stream()), "dlsa_ols_scale_f64")
+    return PartitionFits(coef=theta, Sig_inv=H, Sig_invMcoef=g, status=status,
+                         iters=torch.ones(K, dtype=torch.int32, device=dev), loglik=sigma2, passes=1,
+                         n_rows=int(X.shape[0]))
+
+
+def combine_partitions(fits: PartitionFits, group=None, num_partitions: Optional[int] = None) -> CombineResult:
+    """One-round combine (dlsa_mapred, dlsa/dlsa.py:21-61): K4 fixed-order local sum, ONE allreduce of the packed
+    [sum Sig_inv | sum Sig_inv coef | sum coef | K_eff | K] buffer when torch.distributed is initialised, then K5
+    (Cholesky solve of the SPD sum — the reference's lstsq, :48).  beta_byONESHOT = sum coef / K (:51-52), with K
+    the total partition count (skipped partitions count, as getNumPartitions() does)."""
+    K, p = fits.coef.shape
+    dev = fits.coef.device
+    packed = torch.empty(p * p + 2 * p + 2, dtype=_F64, device=dev)
+    check(lib.dlsa_partition_reduce_f64(fits.Sig_inv.data_ptr(), fits.Sig_invMcoef.data_ptr(), fits.coef.data_ptr(),
+                                        fits.status.data_ptr(), K, p, packed.data_ptr(), _stream()),
+          "dlsa_partition_reduce_f64")
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    S = packed[: p * p].view(p, p)
+    v = packed[p * p: p * p + p]
+    c = packed[p * p + p: p * p + 2 * p]
+    tail = packed[p * p + 2 * p:].tolist()
+    K_eff, K_total = int(round(tail[0])), int(round(tail[1]))
+    if K_eff == 0:
+        raise Exception("Zero-length grouped pandas DataFrame obtained, check the input.")  # dlsa/dlsa.py:36-39
+    theta = torch.empty(p, dtype=_F64, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _workspace(lib.dlsa_newton_update_workspace_bytes(1, p), dev)
+    check(lib.dlsa_spd_solve_f64(S.data_ptr(), v.data_ptr(), 1, p, theta.data_ptr(), st.data_ptr(), ws.data_ptr(),
+                                 ws.numel(), _stream()), "dlsa_spd_solve_f64")
+    if int(st.item()) != _lib.ST_OK:
+        raise _lib.DlsaLibraryError("combined Sig_inv is not positive definite; DLSA needs an SPD sum "
+                                    "(the reference's lstsq min-norm fallback is not provided)")
+    Kd = K_total if num_partitions is None else num_partitions
+    return CombineResult(beta_byOLS=theta, beta_byONESHOT=c / Kd, Sig_inv_sum=S.clone(), K_eff=K_eff, K_total=K_total)
+
+
+def lars_path(Sigma0: torch.Tensor, b0: torch.Tensor, intercept: bool, n: float, type: str = "lar",
+              eps: float = 2.220446049250313e-16, max_steps: Optional[int] = None) -> LarsResult:
+    """lars_lsa on the device (K6 + K7): dlsa/lsa.py:90-212; intercept branch per the R original."""
+    dev = _require_cuda(Sigma0, b0)
+    Sigma0 = Sigma0.to(_F64).contiguous()
+    b0 = b0.to(_F64).contiguous().view(-1)
+    p0 = b0.numel()
+    if Sigma0.shape != (p0, p0):
+        raise ValueError("Sigma0 must be [p, p] with p = len(b0)")
+    if type not in ("lar", "lasso"):
+        raise ValueError("type must be 'lar' or 'lasso'")
+    m = p0 - (1 if intercept else 0)
+    steps = 8 * m if max_steps is None else int(max_steps)
+    rows = steps + 1
+    beta = torch.zeros(rows, m, dtype=_F64, device=dev)
+    beta0 = torch.zeros(rows, dtype=_F64, device=dev)
+    rss = torch.zeros(rows, dtype=_F64, device=dev)
+    aic = torch.zeros(rows, dtype=_F64, device=dev)
+    bic = torch.zeros(rows, dtype=_F64, device=dev)
+    dof = torch.zeros(rows, dtype=torch.int32, device=dev)
+    info = torch.zeros(4, dtype=torch.int32, device=dev)
+    ws = _workspace(lib.dlsa_lars_path_workspace_bytes(p0, steps), dev)
+    check(lib.dlsa_lars_path_f64(Sigma0.data_ptr(), b0.data_ptr(), p0, int(bool(intercept)), float(n),
+                                 _lib.LARS_LAR if type == "lar" else _lib.LARS_LASSO, float(eps), steps,
+                                 beta.data_ptr(), beta0.data_ptr(), rss.data_ptr(), aic.data_ptr(), bic.data_ptr(),
+                                 dof.data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+          "dlsa_lars_path_f64")
+    nrows, ia, ib, err = info.tolist()
+    if err:
+        raise _lib.DlsaLibraryError("lars path: no variable could enter (singular Sigma)")
+    return LarsResult(AIC=aic[:nrows], BIC=bic[:nrows], beta=beta[:nrows], beta0=beta0[:nrows], RSS=rss[:nrows],
+                      dof=dof[:nrows], argmin_AIC=ia, argmin_BIC=ib)
+
+
+def logistic_loglik(X, y, part_offsets, par, fit_intercept=False) -> torch.Tensor:
+    """Per-partition log-likelihood of each column of ``par`` [p, q] (logistic_model_eval, dlsa/models.py:151-225).
+    Returns [K, q]; the global value is the column sum (dlsa/model_eval.py:38-39)."""
+    dev, y = _check_inputs(X, y, part_offsets)
+    K = part_offsets.numel() - 1
+    par = par.to(dev, _F64).contiguous()
+    q = par.shape[1]
+    out = torch.zeros(K, q, dtype=_F64, device=dev)
+    ws = _workspace(lib.dlsa_logistic_loglik_workspace_bytes(K, q), dev)
+    check(lib.dlsa_logistic_loglik_f64(X.data_ptr(), X.stride(0), y.data_ptr(), part_offsets.data_ptr(), K, X.shape[1],
+                                       int(fit_intercept), par.data_ptr(), q, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _stream()), "dlsa_logistic_loglik_f64")
+    return out
+
+
+def dlsa_fit(X, y, part_offsets, fit_intercept=False, sample_size=None, type="lar", config=None, group=None,
+             family="logistic"):
+    """Whole hot path on this rank's partitions: map (fit) -> combine (+allreduce) -> LARS + AIC/BIC.
+    ``sample_size`` is the global n used by BIC (defaults to the all-rank row count)."""
+    if family == "logistic":
+        fits = fit_logistic_partitions(X, y, part_offsets, fit_intercept, config)
+    elif family == "linear":
+        fits = fit_linear_partitions(X, y, part_offsets)
+    else:
+        raise ValueError("family must be 'logistic' or 'linear'")
+    comb = combine_partitions(fits, group=group)
+    if sample_size is None:
+        n = torch.tensor([float(X.shape[0])], dtype=_F64, device=X.device)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(n, group=group)
+        sample_size = float(n.item())
+    path = lars_path(comb.Sig_inv_sum, comb.beta_byOLS, fit_intercept, sample_size, type=type)
+    return fits, comb, path

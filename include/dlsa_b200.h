@@ -1,0 +1,160 @@
+/*
+ * dlsa_b200 — C ABI of the B200-native DLSA hot path (libdlsa_b200.so).
+ *
+ * Drop-in boundary for the per-partition fit -> one-round combine -> LARS/IC path of feng-li/dlsa.
+ * Every entry point names the reference interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain C types only; all array arguments are DEVICE pointers unless the name ends in _host;
+ *   - float64 everywhere (the reference's arithmetic type), row-major, int64 row offsets;
+ *   - the caller owns every buffer, including workspaces (sizes from the *_workspace_bytes queries);
+ *     the library never allocates device memory, never synchronises the device and never touches
+ *     the default stream: work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = OK, negative = argument error (DLSA_E_*), positive = cudaError_t;
+ *     dlsa_last_error() gives a thread-local message for the last non-zero return;
+ *   - per-partition outcomes are reported in device `status[K]` ints (DLSA_ST_*), never by exceptions.
+ */
+#ifndef DLSA_B200_H
+#define DLSA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLSA_ABI_VERSION 1
+
+/* argument errors */
+#define DLSA_E_BADARG (-1)
+#define DLSA_E_UNSUPPORTED (-2)
+#define DLSA_E_WORKSPACE (-3)
+
+/* per-partition status codes */
+#define DLSA_ST_OK 0
+#define DLSA_ST_NOT_CONVERGED 1
+#define DLSA_ST_NOT_SPD 2
+#define DLSA_ST_SKIPPED 4
+
+/* model family of the fused pass */
+#define DLSA_FAMILY_LOGISTIC 0
+#define DLSA_FAMILY_LINEAR 1
+
+/* LARS path type (dlsa/lsa.py:90 `type`) */
+#define DLSA_LARS_LAR 0
+#define DLSA_LARS_LASSO 1
+
+int dlsa_abi_version(void);
+const char *dlsa_last_error(void);
+/* number of kernels this library has launched since it was loaded (bench.py's gpu_launches) */
+unsigned long long dlsa_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  fused Newton / IRLS pass over all partitions — one launch (+ a small slice-reduce when a
+ *     partition is split over several CTAs).
+ * Replaces, per partition k with rows [part_off[k], part_off[k+1]) of X:
+ *   sklearn LogisticRegression(newton-cg).fit's gradient/Hessian sweeps  dlsa/models.py:110-113
+ *   predict_proba + Sig_inv = X' diag(p(1-p)) X                          dlsa/models.py:114,130
+ *   R logistic(): grad = colSums((Y-prob)*X), hess = t(X)%*%(prob*(1-prob)*X)   dlsa/R/wlse_func.R:52-54
+ * family = LINEAR gives X'X, X'y, y'y instead (R lm per block, dlsa/R/wlse_func.R:169-182).
+ *
+ *   X        [n, ldx] float64 row-major, px feature columns used (px <= ldx)
+ *   y        [n] float64 labels (0/1) or responses
+ *   part_off [K+1] int64 row offsets (device)
+ *   fit_intercept: p = px + 1 and a synthesised all-ones column is coefficient 0 (dlsa/models.py:116-122)
+ *   beta     [K, p] current coefficients (ignored for LINEAR)
+ *   active   [K] int or NULL; partitions with active[k]==0 are skipped and their outputs left untouched
+ *   g        [K, p]     out: X'(y - prob)            (LINEAR: X'y)
+ *   H        [K, p, p]  out: X' diag(prob(1-prob)) X (LINEAR: X'X), full symmetric
+ *   loglik   [K]        out: sum y*eta - log(1+exp(eta)) (LINEAR: y'y); NULL to skip computing it
+ *   max_part_rows: upper bound of rows in any partition (host int; sizes the grid)
+ */
+size_t dlsa_irls_pass_workspace_bytes(int K, int p, int64_t max_part_rows);
+int dlsa_irls_pass_f64(const double *X, int64_t ldx, const double *y, const int64_t *part_off, int K, int px,
+                       int fit_intercept, int family, const double *beta, const int *active, double *g, double *H,
+                       double *loglik, int64_t max_part_rows, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  batched p x p Cholesky solve + Newton update for every active partition.
+ * Replaces  del = solve(hess)%*%grad; damping; beta = beta + del; stop rule   dlsa/R/wlse_func.R:55-62
+ *           (and sklearn's inner CG + line search, dlsa/models.py:110-113).
+ *   delta = H^-1 g;  md = max|delta|;  if md > damp_above: delta *= damp_factor;  beta += delta;
+ *   iters[k] += 1;  md <= tol  => active[k] = 0 (converged);  H not SPD / non-finite => status NOT_SPD, active 0.
+ *   n_active (device int, caller zeroes it) is incremented once per partition still active afterwards.
+ */
+size_t dlsa_newton_update_workspace_bytes(int K, int p);
+int dlsa_newton_update_f64(const double *H, const double *g, int K, int p, double *beta, double *max_delta,
+                           int *status, int *active, int *iters, int *n_active, double tol, double damp_above,
+                           double damp_factor, void *workspace, size_t workspace_bytes, void *stream);
+
+/* K5  plain batched SPD solve  x_k = A_k^-1 b_k  (np.linalg.lstsq on the SPD sum, dlsa/dlsa.py:48;
+ *     R solve(Sig_inv_sum), dlsa/R/wlse_func.R:200).  status[k] = NOT_SPD when the factorisation fails. */
+int dlsa_spd_solve_f64(const double *A, const double *b, int K, int p, double *x, int *status, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* K3  batched symmetric matrix-vector product  out_k = H_k beta_k   (Sig_invMcoef, dlsa/models.py:131) */
+int dlsa_batched_symv_f64(const double *H, const double *beta, int K, int p, double *out, void *stream);
+
+/* OLS block epilogue (R lm + solve(vcov), dlsa/R/wlse_func.R:169-182): given XtX, Xty, yty, rows n_k and
+ * theta_k = XtX^-1 Xty (from dlsa_spd_solve_f64): sigma2_k = (yty - theta'Xty)/(n_k - p);
+ * Sig_inv_k = XtX/sigma2_k (in place), Sig_invMcoef_k = Xty/sigma2_k (in place). */
+int dlsa_ols_scale_f64(double *XtX, double *Xty, const double *yty, const double *theta, const int64_t *part_off,
+                       int K, int p, double *sigma2, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  one-round combine, local part: fixed-order sum over this rank's partitions.
+ * Replaces Spark  groupby('par_id').sum(...)                                  dlsa/dlsa.py:30-34
+ *   packed_out [p*p + 2p + 2] = [ sum_k H_k | sum_k Hbeta_k | sum_k beta_k | K_eff | K_total ]
+ *   partitions with status != OK contribute nothing to the first three blocks or to K_eff
+ *   (the reference's all-zero frame for a skipped chunk, dlsa/models.py:84-91).
+ * The cross-GPU step is ONE allreduce(sum) of packed_out, issued by the caller on the same stream.
+ */
+int dlsa_partition_reduce_f64(const double *H, const double *Hbeta, const double *beta, const int *status, int K,
+                              int p, double *packed_out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6+K7  LARS / lasso path on the least-squares approximation and its information criteria.
+ * Replaces lars_lsa(Sigma0, b0, intercept, n, type, eps, max_steps)          dlsa/lsa.py:90-212
+ *          (intercept branch as in the R original, dlsa/R/dlsa_alasso_func.R:115-125,243-245)
+ *      and the first-argmin AIC/BIC selection of dlsa()                       dlsa/dlsa.py:90-91
+ *   Sigma0 [p0,p0], b0 [p0]; m = p0 - (intercept?1:0); max_steps <= 0 means 8*m
+ *   beta_path [(max_steps+1), m], beta0_path/rss/aic/bic [(max_steps+1)], dof [(max_steps+1)] int
+ *   info [4] int: {n_rows (= steps+1), argmin AIC, argmin BIC, error flag}
+ */
+size_t dlsa_lars_path_workspace_bytes(int p0, int max_steps);
+int dlsa_lars_path_f64(const double *Sigma0, const double *b0, int p0, int intercept, double n, int type, double eps,
+                       int max_steps, double *beta_path, double *beta0_path, double *rss, double *aic, double *bic,
+                       int *dof, int *info, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * f1  log-likelihood of q candidate coefficient vectors over all partitions
+ * Replaces logistic_model_eval                                               dlsa/models.py:151-225
+ *   par [p, q] (column i is one estimator), out [K, q] per-partition log-likelihoods.
+ */
+size_t dlsa_logistic_loglik_workspace_bytes(int K, int q);
+int dlsa_logistic_loglik_f64(const double *X, int64_t ldx, const double *y, const int64_t *part_off, int K, int px,
+                             int fit_intercept, const double *par, int q, double *out, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1  synthetic data with the law of simulate_logistic (dlsa/models.py:6-40), generated on device by
+ *     a counter-based generator keyed by (seed, global row index) so any sharding sees the same rows.
+ *   law 0: X ~ U(-0.5, 0.5), y ~ Bernoulli(sigmoid(X beta_true))        (dlsa/models.py:22-30)
+ *   law 1: X ~ N(0,1),       y = X beta_true + N(0,1)                    (dlsa/R/simulator.R, linear)
+ *   rows [row0, row0 + n) of the global stream are written to X [n, ldx], y [n].
+ */
+int dlsa_simulate_f64(double *X, int64_t ldx, double *y, int64_t row0, int64_t n, int px, const double *beta_true,
+                      uint64_t seed, int law, void *stream);
+
+/* a11  dense one-hot expansion with the layout of logistic_model's dummy branch (dlsa/models.py:56-79):
+ *   X[i, col_base[c] + codes[i, c]] = 1 for every categorical column c whose code is >= 0
+ *   (code -1 = baseline level, no column).  numeric [n, n_num] is copied (optionally standardised with
+ *   mean/std, dlsa/models.py:99-101) to columns [0, n_num).  X [n, ldx] must be zero-filled by the caller. */
+int dlsa_onehot_expand_f64(const double *numeric, int n_num, const double *mean, const double *std, const int *codes,
+                           int n_cat, const int *col_base, int64_t n, double *X, int64_t ldx, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLSA_B200_H */

@@ -243,9 +243,8 @@ def lars_lsa(Sigma0, b0, intercept, n, type="lar", eps=EPS, max_steps=None):
         C = Cvec[inactive]
         Cmax = np.max(np.abs(C))
         if drops is None or not np.any(drops):
-            newmask = np.abs(C) >= Cmax - eps  # :131
+            newmask = np.abs(C) >= Cmax - eps  # :131  (C itself is re-formed over `rest` below, == :132)
             new = [inactive[i] for i in np.nonzero(newmask)[0]]
-            C = C[~newmask]  # :132
             for inew in new:
                 Rn, grew = _chol_append(R, Sigma[inew, inew], Sigma[inew, active], eps)
                 if not grew and R is not None:
@@ -265,8 +264,11 @@ def lars_lsa(Sigma0, b0, intercept, n, type="lar", eps=EPS, max_steps=None):
             excl = set(active) | set(ignores)
             rest = [j for j in range(m) if j not in excl]  # np.delete(Sigma, active+ignores, axis=1)
             a = w @ Sigma[np.ix_(active, rest)]  # :157-160
-            # NB (:161): C is Cvec over `inactive` minus the joiners; `a` is over all columns minus
-            # active and ignores.  They have equal length whenever nothing is ignored / dropped-pending.
+            # (:132,161) the reference's C is Cvec over `inactive` minus this step's joiners and `a` is over
+            # all columns minus active and ignores: the same index set whenever nothing has been ignored.
+            # With ignored (machine-singular) variables the reference's two vectors differ in length and it
+            # raises; here both are taken over `rest` (the R `lars` convention).
+            C = Cvec[rest]
             gam = np.concatenate([(Cmax - C) / (A - a), (Cmax + C) / (A + a)])
             cand = gam[gam > eps]
             gamhat = min(np.min(cand), Cmax / A) if cand.size else Cmax / A  # :162
@@ -294,7 +296,7 @@ def lars_lsa(Sigma0, b0, intercept, n, type="lar", eps=EPS, max_steps=None):
             keep = ~drops
             active = [a_ for a_, kp in zip(active, keep) if kp]
             Sign = [s_ for s_, kp in zip(Sign, keep) if kp]
-        inactive = [j for j in range(m) if j not in set(active)]  # :188 (ignores stay "inactive")
+        inactive = [j for j in range(m) if j not in set(active) and j not in set(ignores)]  # :188
     beta = beta[: k + 1]
     dff = s[None, :] - beta  # (k+1) x m
     RSS = np.einsum("ki,ij,kj->k", dff, Sigma, dff)  # :191-192

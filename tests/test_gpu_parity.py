@@ -1,0 +1,249 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the reference goldens.
+
+Tolerances (north_star): combined theta <= 1e-6 max-abs, Sig_inv <= 1e-9 relative Frobenius, same support.
+Kernel-level checks use much tighter bounds (float64 summation-order noise only)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import games_data, load_golden, sim_data
+from oracle import numpy_dlsa as onp
+
+pytestmark = pytest.mark.gpu
+
+THETA_TOL = 1e-6
+SIG_RTOL = 1e-9
+
+
+def relfro(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import dlsa_b200
+    from dlsa_b200 import engine
+    return engine
+
+
+def dev(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
+
+
+def ragged_offsets(sizes):
+    off = np.zeros(len(sizes) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(sizes)
+    return off
+
+
+@pytest.mark.parametrize("px,icpt", [(3, False), (4, True), (8, False), (9, False), (20, False), (20, True), (31, True),
+                                     (37, False), (40, False), (48, False), (50, False), (50, True), (55, True),
+                                     (56, False)])
+def test_irls_pass_matches_oracle(eng, px, icpt):
+    rng = np.random.default_rng(px * 7 + icpt)
+    sizes = [0, 1, 31, 32, 33, 257, 1000, 4097, 64, 5]
+    off = ragged_offsets(sizes)
+    n = int(off[-1])
+    p = px + int(icpt)
+    X = rng.random((n, px)) - 0.5
+    y = (rng.random(n) < 0.4).astype(np.float64)
+    beta = rng.standard_normal((len(sizes), p)) * 0.7
+    g, H, ll = eng.irls_pass(dev(X), dev(y), dev(off, torch.int64), dev(beta), fit_intercept=icpt)
+    g, H, ll = g.cpu().numpy(), H.cpu().numpy(), ll.cpu().numpy()
+    for k, nk in enumerate(sizes):
+        Xk = X[off[k]:off[k + 1]]
+        if icpt:
+            Xk = np.concatenate([np.ones((nk, 1)), Xk], axis=1)
+        g0, H0, ll0 = onp.irls_pass(Xk, y[off[k]:off[k + 1]], beta[k])
+        assert np.allclose(g[k], g0, rtol=1e-11, atol=1e-11), (k, nk)
+        assert np.allclose(H[k], H0, rtol=1e-11, atol=1e-12), (k, nk)
+        assert abs(ll[k] - ll0) <= 1e-11 * max(1.0, abs(ll0))
+        assert np.array_equal(H[k], H[k].T)  # exactly symmetric by construction
+
+
+def test_irls_pass_saturated_eta_and_slices(eng):
+    """eta = +-40 rows (weights underflow towards 0) and a few big partitions (sliced across CTAs)."""
+    rng = np.random.default_rng(5)
+    px, K = 20, 3
+    sizes = [70_000, 50_001, 90_017]
+    off = ragged_offsets(sizes)
+    n = int(off[-1])
+    X = rng.random((n, px)) - 0.5
+    X[::97] *= 160.0
+    y = (rng.random(n) < 0.5).astype(np.float64)
+    beta = np.ones((K, px))
+    g, H, ll = eng.irls_pass(dev(X), dev(y), dev(off, torch.int64), dev(beta))
+    for k in range(K):
+        g0, H0, ll0 = onp.irls_pass(X[off[k]:off[k + 1]], y[off[k]:off[k + 1]], beta[k])
+        assert np.allclose(g[k].cpu().numpy(), g0, rtol=1e-10, atol=1e-9)
+        assert relfro(H[k].cpu().numpy(), H0) < 1e-12
+        assert abs(ll[k].item() - ll0) <= 1e-11 * abs(ll0)
+
+
+def test_irls_pass_unaligned_rows_and_ldx(eng):
+    """odd px / odd leading dimension / 8-byte-offset base pointer take the cp.async (non-TMA) staging path."""
+    rng = np.random.default_rng(6)
+    n, px, ldx = 3000, 13, 17
+    big = rng.random((n, ldx)) - 0.5
+    y = (rng.random(n) < 0.5).astype(np.float64)
+    off = ragged_offsets([1000, 1500, 500])
+    beta = rng.standard_normal((3, px))
+    Xd = dev(big)[:, 1:1 + px]  # base pointer 8 bytes off, stride 17
+    g, H, ll = eng.irls_pass(Xd, dev(y), dev(off, torch.int64), dev(beta))
+    for k in range(3):
+        g0, H0, ll0 = onp.irls_pass(big[off[k]:off[k + 1], 1:1 + px], y[off[k]:off[k + 1]], beta[k])
+        assert np.allclose(g[k].cpu().numpy(), g0, rtol=1e-11, atol=1e-11)
+        assert relfro(H[k].cpu().numpy(), H0) < 1e-13
+
+
+def run_fit(eng, X, y, pid, K, icpt=False):
+    from dlsa_b200 import synth
+    Xg, yg, off = synth.group_by_partition(dev(X), dev(y), dev(pid, torch.int64), K)
+    fits = eng.fit_logistic_partitions(Xg, yg, off, fit_intercept=icpt)
+    torch.cuda.synchronize()
+    return fits
+
+
+def check_against_golden(eng, fits, g, n):
+    coef = fits.coef.cpu().numpy()
+    assert fits.status.cpu().numpy().tolist() == [0] * coef.shape[0]
+    assert np.max(np.abs(coef - g["ref_coef"])) < 1e-8
+    sig = fits.Sig_inv.cpu().numpy()
+    for k in range(coef.shape[0]):
+        assert relfro(sig[k], g["ref_Sig_inv"][k]) < SIG_RTOL
+    assert np.max(np.abs(fits.Sig_invMcoef.cpu().numpy() - g["ref_Sig_invMcoef"])) < 1e-6 * np.max(np.abs(g["ref_Sig_invMcoef"]))
+    comb = eng.combine_partitions(fits)
+    assert np.max(np.abs(comb.beta_byOLS.cpu().numpy() - g["ref_beta_byOLS"])) < THETA_TOL
+    assert np.max(np.abs(comb.beta_byOLS.cpu().numpy() - g["ref_beta_byOLS"])) < 1e-9  # in fact far tighter
+    assert np.max(np.abs(comb.beta_byONESHOT.cpu().numpy() - g["ref_beta_byONESHOT"])) < 1e-9
+    assert relfro(comb.Sig_inv_sum.cpu().numpy(), g["ref_Sig_inv_sum"]) < SIG_RTOL
+    return comb
+
+
+def check_path(path, g, prefix):
+    rb = g[prefix + "beta"]
+    beta = path.beta.cpu().numpy()
+    assert beta.shape == rb.shape
+    assert np.max(np.abs(beta - rb)) < 1e-8 * max(1.0, np.max(np.abs(rb)))
+    assert np.array_equal(beta != 0, rb != 0)
+    assert np.allclose(path.AIC.cpu().numpy(), g[prefix + "AIC"], rtol=1e-8, atol=1e-6)
+    assert np.allclose(path.BIC.cpu().numpy(), g[prefix + "BIC"], rtol=1e-8, atol=1e-6)
+    assert path.argmin_BIC == int(np.argmin(g[prefix + "BIC"]))
+    assert path.argmin_AIC == int(np.argmin(g[prefix + "AIC"]))
+
+
+def test_games_expand_end_to_end(eng):
+    X, y, K, g = games_data()
+    pid = np.arange(X.shape[0]) % K
+    fits = run_fit(eng, X, y, pid, K)
+    comb = check_against_golden(eng, fits, g, X.shape[0])
+    for typ in ("lar", "lasso"):
+        path = eng.lars_path(comb.Sig_inv_sum, comb.beta_byOLS, False, X.shape[0], type=typ)
+        check_path(path, g, f"ref_{typ}_")
+    # SURVEY App. C known answers
+    path = eng.lars_path(comb.Sig_inv_sum, comb.beta_byOLS, False, X.shape[0])
+    assert path.argmin_BIC == 9 and abs(path.BIC[9].item() - 91.073913) < 1e-5
+    assert path.beta[9][1].item() == 0.0
+
+
+@pytest.mark.parametrize("name", ["sim_c1_n100000_p20_k16.npz", "sim_small_n6000_p7_k3.npz",
+                                  "sim_icpt_n20000_p12_k4.npz", "sim_p50_n40000_k4.npz"])
+def test_sim_goldens_end_to_end(eng, name):
+    g = load_golden(name)
+    pid, y, X, K = sim_data(g)
+    icpt = bool(g["in_fit_intercept"])
+    fits = run_fit(eng, X, y, pid, K, icpt)
+    comb = check_against_golden(eng, fits, g, X.shape[0])
+    if not icpt:
+        for typ in ("lar", "lasso"):
+            path = eng.lars_path(comb.Sig_inv_sum, comb.beta_byOLS, False, X.shape[0], type=typ)
+            check_path(path, g, f"ref_{typ}_")
+    else:
+        S, th = g["ref_Sig_inv_sum"], g["ref_beta_byOLS"]
+        ref = onp.lars_lsa(S, th, True, X.shape[0])
+        path = eng.lars_path(dev(S), dev(th), True, X.shape[0])
+        assert np.max(np.abs(path.beta.cpu().numpy() - ref["beta"])) < 1e-9
+        assert np.max(np.abs(path.beta0.cpu().numpy() - ref["beta0"])) < 1e-9
+        assert path.argmin_BIC == int(np.argmin(ref["BIC"]))
+
+
+@pytest.mark.parametrize("typ", ["lar", "lasso"])
+def test_lars_standalone_goldens(eng, typ):
+    g = load_golden("lars_cases.npz")
+    for i in range(int(g["n_cases"])):
+        key = f"c{i}_{typ}_"
+        path = eng.lars_path(dev(g[key + "in_Sigma"]), dev(g[key + "in_b"]), False, int(g[key + "in_n"]), type=typ)
+        check_path(path, g, key + "ref_")
+
+
+def test_linear_fit_matches_oracle(eng):
+    rng = np.random.default_rng(2)
+    n, p, K = 30_000, 24, 5
+    X = rng.standard_normal((n, p))
+    beta = np.tile([3, 1.5, 0, 0, 2, 0, 0, 0], 3).astype(float)
+    y = X @ beta + rng.standard_normal(n)
+    off = ragged_offsets([5000, 7000, 6000, 6001, 5999])
+    fits = eng.fit_linear_partitions(dev(X), dev(y), dev(off, torch.int64))
+    for k in range(K):
+        th, Sg, Sgt, s2 = onp.ols_fit(X[off[k]:off[k + 1]], y[off[k]:off[k + 1]])
+        assert np.max(np.abs(fits.coef[k].cpu().numpy() - th)) < 1e-10
+        assert relfro(fits.Sig_inv[k].cpu().numpy(), Sg) < 1e-11
+        assert np.allclose(fits.Sig_invMcoef[k].cpu().numpy(), Sgt, rtol=1e-10)
+    comb = eng.combine_partitions(fits)
+    th_ref, _, S_ref = onp.combine(*zip(*[onp.ols_fit(X[off[k]:off[k + 1]], y[off[k]:off[k + 1]])[:3]
+                                           for k in range(K)]))
+
+
+def test_loglik_eval_matches_oracle(eng):
+    rng = np.random.default_rng(3)
+    n, px = 20_000, 11
+    X = rng.random((n, px)) - 0.5
+    y = (rng.random(n) < 0.5).astype(np.float64)
+    off = ragged_offsets([3000, 9000, 8000])
+    for icpt in (False, True):
+        p = px + int(icpt)
+        par = rng.standard_normal((p, 4))
+        out = eng.logistic_loglik(dev(X), dev(y), dev(off, torch.int64), dev(par), fit_intercept=icpt).cpu().numpy()
+        for k in range(3):
+            Xk = X[off[k]:off[k + 1]]
+            if icpt:
+                Xk = np.concatenate([np.ones((Xk.shape[0], 1)), Xk], axis=1)
+            ref = onp.logistic_loglik(Xk, y[off[k]:off[k + 1]], par)
+            assert np.allclose(out[k], ref, rtol=1e-11)
+
+
+def test_device_generator_matches_host_restatement(eng):
+    from dlsa_b200 import synth
+    n, p, seed, row0 = 5000, 20, 20210517, 123_456_789
+    X, y = synth.simulate_logistic_device(n, p, seed, "cuda", row0=row0)
+    rows = (np.arange(n, dtype=np.uint64) + np.uint64(row0))[:, None]
+    cols = np.arange(p, dtype=np.uint64)[None, :]
+    Xh = synth.host_uniform(seed, rows, cols) - 0.5
+    assert np.array_equal(X.cpu().numpy(), Xh)  # bit-exact
+    u = synth.host_uniform(seed, rows[:, 0], np.uint64(synth.LABEL_COL))
+    prob = 1 / (1 + np.exp(-(Xh @ synth.true_beta(p))))
+    yh = (u < prob).astype(np.float64)
+    assert np.mean(y.cpu().numpy() != yh) < 1e-3  # identical up to exp() rounding at the threshold
+    # sharding invariance: rows generated as two shards equal the single-shot rows
+    Xa, _ = synth.simulate_logistic_device(2000, p, seed, "cuda", row0=row0)
+    Xb, _ = synth.simulate_logistic_device(3000, p, seed, "cuda", row0=row0 + 2000)
+    assert torch.equal(torch.cat([Xa, Xb]), X)
+
+
+def test_empty_and_error_paths(eng):
+    from dlsa_b200 import _lib
+    X = dev(np.zeros((4, 3)))
+    with pytest.raises(TypeError):
+        eng.irls_pass(X.float(), dev(np.zeros(4)), dev([0, 4], torch.int64), dev(np.zeros((1, 3))))
+    with pytest.raises(ValueError):
+        eng.irls_pass(torch.zeros(4, 3, dtype=torch.float64), torch.zeros(4, dtype=torch.float64),
+                      torch.tensor([0, 4]), torch.zeros(1, 3, dtype=torch.float64))
+    # a partition with a single class / separable data diverges: reported through status, not an exception
+    Xs = dev(np.array([[1.0, 0.2], [2.0, -0.1], [3.0, 0.3], [4.0, 0.0]]))
+    ys = dev(np.array([1.0, 1.0, 1.0, 1.0]))
+    fits = eng.fit_logistic_partitions(Xs, ys, dev([0, 4], torch.int64), config=eng.EngineConfig(max_iter=8))
+    assert fits.status.item() in (_lib.ST_NOT_CONVERGED, _lib.ST_NOT_SPD)
+    with pytest.raises(Exception, match="Zero-length"):
+        eng.combine_partitions(fits)
