@@ -17,6 +17,10 @@ from ._lib import lib, check
 
 _F64 = torch.float64
 
+# bench.py sets this to a list to collect (start_event, end_event, rows) around every fused pass launch,
+# recorded on the stream the kernel is launched on.  None = no timing overhead.
+PASS_EVENTS = None
+
 
 @dataclasses.dataclass
 class EngineConfig:
@@ -119,10 +123,16 @@ def irls_pass(X, y, part_offsets, beta, fit_intercept=False, family=_lib.FAMILY_
     need = lib.dlsa_irls_pass_workspace_bytes(K, p, max_part_rows)
     if workspace is None or workspace.numel() < need:
         workspace = _workspace(need, dev)
+    if PASS_EVENTS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.dlsa_irls_pass_f64(X.data_ptr(), X.stride(0), y.data_ptr(), part_offsets.data_ptr(), K, px,
                                  int(fit_intercept), family, _ptr(beta), _ptr(active), g.data_ptr(), H.data_ptr(),
                                  _ptr(ll), max_part_rows, workspace.data_ptr(), workspace.numel(), _stream()),
           "dlsa_irls_pass_f64")
+    if PASS_EVENTS is not None:
+        e1.record()
+        PASS_EVENTS.append((e0, e1, active is None))
     return g, H, ll
 
 
