@@ -247,3 +247,93 @@ def test_empty_and_error_paths(eng):
     assert fits.status.item() in (_lib.ST_NOT_CONVERGED, _lib.ST_NOT_SPD)
     with pytest.raises(Exception, match="Zero-length"):
         eng.combine_partitions(fits)
+
+
+@pytest.mark.parametrize("px,icpt,sizes", [(57, False, [700, 33, 0, 1500]), (100, False, [3000, 1001]),
+                                           (181, True, [2500, 999]), (181, False, [1200]), (182, False, [1500, 700]),
+                                           (200, False, [900]), (256, True, [1100]), (500, False, [1300, 600])])
+def test_irls_pass_large_p_matches_oracle(eng, px, icpt, sizes):
+    """p > 56 goes through the CTA-tiled kernel (several tile groups at p >= 200)."""
+    rng = np.random.default_rng(px + icpt)
+    off = ragged_offsets(sizes)
+    n = int(off[-1])
+    p = px + int(icpt)
+    X = rng.random((n, px)) - 0.5
+    y = (rng.random(n) < 0.4).astype(np.float64)
+    beta = rng.standard_normal((len(sizes), p)) * (2.0 / np.sqrt(p))
+    g, H, ll = eng.irls_pass(dev(X), dev(y), dev(off, torch.int64), dev(beta), fit_intercept=icpt)
+    g, H, ll = g.cpu().numpy(), H.cpu().numpy(), ll.cpu().numpy()
+    for k, nk in enumerate(sizes):
+        Xk = X[off[k]:off[k + 1]]
+        if icpt:
+            Xk = np.concatenate([np.ones((nk, 1)), Xk], axis=1)
+        g0, H0, ll0 = onp.irls_pass(Xk, y[off[k]:off[k + 1]], beta[k])
+        assert np.allclose(g[k], g0, rtol=1e-10, atol=1e-10), (k, nk)
+        assert relfro(H[k], H0) < 1e-13 if nk else np.all(H[k] == 0)
+        assert abs(ll[k] - ll0) <= 1e-11 * max(1.0, abs(ll0))
+        assert np.array_equal(H[k], H[k].T)
+
+
+def test_large_p_sliced_partitions(eng):
+    """few big partitions at p=100: slices + fixed-order slice reduce."""
+    rng = np.random.default_rng(9)
+    px, sizes = 100, [40_000, 25_003]
+    off = ragged_offsets(sizes)
+    X = rng.random((int(off[-1]), px)) - 0.5
+    y = (rng.random(int(off[-1])) < 0.5).astype(np.float64)
+    beta = rng.standard_normal((2, px)) * 0.2
+    g, H, ll = eng.irls_pass(dev(X), dev(y), dev(off, torch.int64), dev(beta))
+    for k in range(2):
+        g0, H0, ll0 = onp.irls_pass(X[off[k]:off[k + 1]], y[off[k]:off[k + 1]], beta[k])
+        assert np.allclose(g[k].cpu().numpy(), g0, rtol=1e-10, atol=1e-9)
+        assert relfro(H[k].cpu().numpy(), H0) < 1e-13
+        assert abs(ll[k].item() - ll0) <= 1e-11 * abs(ll0)
+
+
+def test_airline_shaped_fit_p182(eng):
+    """C3-shaped miniature: intercept + 7 numerics + 174 one-hot dummies (p = 182), 3 partitions."""
+    rng = np.random.default_rng(10)
+    n = 60_000
+    num = rng.standard_normal((n, 7))
+    cards = [11, 6, 7, 75, 75]  # levels minus baseline
+    cols = [num]
+    for c in cards:
+        w = 1.0 / np.arange(1, c + 2)
+        lv = rng.choice(c + 1, size=n, p=w / w.sum())
+        oh = np.zeros((n, c))
+        m = lv > 0
+        oh[np.nonzero(m)[0], lv[m] - 1] = 1.0
+        cols.append(oh)
+    X = np.concatenate(cols, axis=1)
+    assert X.shape[1] == 181
+    beta = rng.standard_normal(182) * 0.3 * (rng.random(182) < 0.4)
+    beta[0] = -1.0
+    y = (rng.random(n) < 1 / (1 + np.exp(-(beta[0] + X @ beta[1:])))).astype(np.float64)
+    off = ragged_offsets([20_000, 20_000, 20_000])
+    fits = eng.fit_logistic_partitions(dev(X), dev(y), dev(off, torch.int64), fit_intercept=True)
+    assert fits.status.cpu().tolist() == [0, 0, 0]
+    for k in range(3):
+        c0, S0, _ = onp.logistic_fit(X[off[k]:off[k + 1]], y[off[k]:off[k + 1]], fit_intercept=True)
+        assert np.max(np.abs(fits.coef[k].cpu().numpy() - c0)) < 1e-7
+        assert relfro(fits.Sig_inv[k].cpu().numpy(), S0) < SIG_RTOL
+    comb = eng.combine_partitions(fits)
+    path = eng.lars_path(comb.Sig_inv_sum, comb.beta_byOLS, True, n)
+    ref = onp.lars_lsa(comb.Sig_inv_sum.cpu().numpy(), comb.beta_byOLS.cpu().numpy(), True, n)
+    assert path.beta.shape == ref["beta"].shape
+    assert np.max(np.abs(path.beta.cpu().numpy() - ref["beta"])) < 1e-7
+    assert path.argmin_BIC == int(np.argmin(ref["BIC"]))
+    assert np.array_equal(path.beta[path.argmin_BIC].cpu().numpy() != 0, ref["beta"][path.argmin_BIC] != 0)
+
+
+def test_linear_p100_matches_oracle(eng):
+    rng = np.random.default_rng(12)
+    n, p = 24_000, 100
+    X = rng.standard_normal((n, p))
+    beta = np.tile([3, 1.5, 0, 0, 2, 0, 0, 0, 0, 0], 10).astype(float)
+    y = X @ beta + rng.standard_normal(n)
+    off = ragged_offsets([8000, 9000, 7000])
+    fits = eng.fit_linear_partitions(dev(X), dev(y), dev(off, torch.int64))
+    for k in range(3):
+        th, Sg, Sgt, s2 = onp.ols_fit(X[off[k]:off[k + 1]], y[off[k]:off[k + 1]])
+        assert np.max(np.abs(fits.coef[k].cpu().numpy() - th)) < 1e-10
+        assert relfro(fits.Sig_inv[k].cpu().numpy(), Sg) < 1e-11
