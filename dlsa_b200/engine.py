@@ -12,7 +12,7 @@ from typing import Optional
 
 import torch
 
-from . import _lib
+from . import _lib, parallel
 from ._lib import lib, check
 
 _F64 = torch.float64
@@ -220,14 +220,8 @@ def combine_partitions(fits: PartitionFits, group=None, num_partitions: Optional
     check(lib.dlsa_partition_reduce_f64(fits.Sig_inv.data_ptr(), fits.Sig_invMcoef.data_ptr(), fits.coef.data_ptr(),
                                         fits.status.data_ptr(), K, p, packed.data_ptr(), _stream()),
           "dlsa_partition_reduce_f64")
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-    S = packed[: p * p].view(p, p)
-    v = packed[p * p: p * p + p]
-    c = packed[p * p + p: p * p + 2 * p]
-    tail = packed[p * p + 2 * p:].tolist()
-    K_eff, K_total = int(round(tail[0])), int(round(tail[1]))
+    parallel.allreduce_packed(packed, group)  # the one collective of the whole algorithm
+    S, v, c, K_eff, K_total = parallel.unpack(packed, p)
     if K_eff == 0:
         raise Exception("Zero-length grouped pandas DataFrame obtained, check the input.")  # dlsa/dlsa.py:36-39
     theta = torch.empty(p, dtype=_F64, device=dev)

@@ -1,0 +1,130 @@
+"""``dlsa.models`` drop-in: ``simulate_logistic``, ``logistic_model``, ``logistic_model_eval`` (+ ``linear_model``).
+
+Frames in, frames out, with the reference's signatures, column names and row order (dlsa/models.py); every number
+is computed by the CUDA kernels behind include/dlsa_b200.h.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import engine, synth
+from .dummies import ChunkMissingDummies, design_columns, encode_design
+from .lsa import _device
+
+
+def simulate_logistic(sample_size, p, partition_method, partition_num, seed=0):
+    """dlsa/models.py:6-40: frame ``[partition_id, label, x0..x{p-1}]`` with X~U(-.5,.5), beta = 1 on the first
+    int(0.4 p) coordinates, label~Bernoulli(sigmoid(X beta)), partition_id = i % K.  Generated on the device
+    (counter-based, seeded) instead of the reference's quadratic row loop over the global NumPy RNG."""
+    if partition_method != "systematic":
+        raise Exception("No such partition method implemented!")  # dlsa/models.py:34-35
+    X, y = synth.simulate_logistic_device(int(sample_size), int(p), int(seed), _device())
+    pid = np.arange(sample_size, dtype=np.float64) % partition_num
+    data = np.concatenate([pid[:, None], y.cpu().numpy()[:, None], X.cpu().numpy()], axis=1)
+    return pd.DataFrame(data, columns=["partition_id", "label"] + ["x" + str(i) for i in range(p)])
+
+
+def _design(sample_df, Y_name, fit_intercept, dummy_info, dummy_factors_baseline, data_info, strict=True):
+    dev = _device()
+    X, names = encode_design(sample_df, Y_name, dummy_info, list(dummy_factors_baseline), data_info, dev, strict=strict)
+    y = torch.as_tensor(np.array(sample_df[Y_name].to_numpy(dtype=np.float64), copy=True), device=dev)
+    return X, y, names
+
+
+def _frame(coef, smc, sig, names, par_id=None):
+    p = coef.shape[0]
+    out = pd.DataFrame(np.concatenate([coef[:, None], smc[:, None], sig], axis=1),
+                       columns=["coef", "Sig_invMcoef"] + list(names))
+    out.insert(0, "par_id", np.arange(p) if par_id is None else par_id)
+    return out
+
+
+def logistic_model(sample_df, Y_name, fit_intercept=False, dummy_info=[], dummy_factors_baseline=[], data_info=[],
+                   config=None):
+    """Run the logistic model on one partition (dlsa/models.py:42-147) and return its p x (3+p) frame
+    ``['par_id', 'coef', 'Sig_invMcoef'] + X column names`` (intercept first), ``par_id = 0..p-1`` (:136-142).
+
+    A chunk whose dummy columns differ from the expected set gives the reference's warning and all-zero frame
+    (:84-91).  A fit that does not converge / is not positive definite raises ``ValueError`` (the reference surfaces
+    sklearn's exceptions and ConvergenceWarning in that situation)."""
+    sample_df = sample_df.reset_index(drop=True)
+    icpt = ["intercept"] if fit_intercept else []
+    try:
+        X, y, names = _design(sample_df, Y_name, fit_intercept, dummy_info, dummy_factors_baseline, data_info)
+    except ChunkMissingDummies as ex:
+        names = design_columns(list(sample_df.columns), Y_name, dummy_info, dummy_factors_baseline, False)
+        warnings.warn("Dummies:" + str(ex.missing) + "missing in this data chunk " + str(ex.shape)
+                      + "Skip modeling this part of data.")
+        return pd.DataFrame(0, index=np.arange(len(icpt + names)), columns=["par_id", "coef", "Sig_invMcoef"] + icpt + names)
+    off = torch.tensor([0, X.shape[0]], dtype=torch.int64, device=X.device)
+    fits = engine.fit_logistic_partitions(X, y, off, fit_intercept=fit_intercept, config=config)
+    st = int(fits.status.item())
+    if st != 0:
+        raise ValueError(f"logistic_model: partition fit failed (status {st}: "
+                         f"{'not converged' if st == 1 else 'Hessian not positive definite'}); "
+                         "single-class or separable data has no finite MLE")
+    out = _frame(fits.coef[0].cpu().numpy(), fits.Sig_invMcoef[0].cpu().numpy(), fits.Sig_inv[0].cpu().numpy(),
+                 icpt + names)
+    if out.isna().values.any():
+        warnings.warn("NAs appear in the final output")  # dlsa/models.py:144-145
+    return out
+
+
+def logistic_model_partitions(data_df, Y_name, fit_intercept=False, dummy_info=[], dummy_factors_baseline=[],
+                              data_info=[], config=None, return_fits=False):
+    """The whole map phase in one call: the equivalent of
+    ``data_sdf.groupby("partition_id").apply(logistic_model_udf)`` (projects/logistic_dlsa.py:305-316).
+    Returns the union of the per-partition frames (K*p rows, partitions in ascending ``partition_id`` order), or
+    the tensor-level ``PartitionFits`` with ``return_fits=True``."""
+    data_df = data_df.reset_index(drop=True)
+    icpt = ["intercept"] if fit_intercept else []
+    X, y, names = _design(data_df, Y_name, fit_intercept, dummy_info, dummy_factors_baseline, data_info)
+    pid_vals, pid_codes = np.unique(data_df["partition_id"].to_numpy(), return_inverse=True)
+    K = len(pid_vals)
+    Xg, yg, off = synth.group_by_partition(X, y, torch.as_tensor(pid_codes, device=X.device), K)
+    fits = engine.fit_logistic_partitions(Xg, yg, off, fit_intercept=fit_intercept, config=config)
+    if return_fits:
+        return fits, icpt + names
+    coef, smc, sig = fits.coef.cpu().numpy(), fits.Sig_invMcoef.cpu().numpy(), fits.Sig_inv.cpu().numpy()
+    status = fits.status.cpu().numpy()
+    frames = []
+    for k in range(K):
+        if status[k] != 0:
+            warnings.warn(f"partition {pid_vals[k]}: fit failed (status {status[k]}); returning a zero frame")
+            frames.append(pd.DataFrame(0, index=np.arange(coef.shape[1]), columns=["par_id", "coef", "Sig_invMcoef"] + icpt + names))
+        else:
+            frames.append(_frame(coef[k], smc[k], sig[k], icpt + names))
+    return pd.concat(frames, axis=0, ignore_index=True)
+
+
+def logistic_model_eval(sample_df, Y_name, par, fit_intercept=False, dummy_info=[], dummy_factors_baseline=[],
+                        data_info=[]):
+    """Log-likelihood of every column of ``par`` on one partition (dlsa/models.py:151-225): a one-row frame whose
+    columns are ``par.columns``.  Chunks with missing dummy levels are evaluated with those columns at 0 (:189-197)."""
+    sample_df = sample_df.reset_index(drop=True)
+    try:
+        X, y, names = _design(sample_df, Y_name, fit_intercept, dummy_info, dummy_factors_baseline, data_info)
+    except ChunkMissingDummies as ex:
+        warnings.warn("Dummies:" + str(ex.missing) + "missing in this data chunk " + str(ex.shape))
+        X, y, names = _design(sample_df, Y_name, fit_intercept, dummy_info, dummy_factors_baseline, data_info, strict=False)
+    off = torch.tensor([0, X.shape[0]], dtype=torch.int64, device=X.device)
+    P = torch.as_tensor(np.ascontiguousarray(np.asarray(par, dtype=np.float64)), device=X.device)
+    ll = engine.logistic_loglik(X, y, off, P, fit_intercept=fit_intercept)[0].cpu().numpy()
+    return pd.DataFrame({c: [v] for c, v in zip(par.columns, ll)})
+
+
+def linear_model(sample_df, Y_name, dummy_factors_baseline=[]):
+    """OLS on one partition in the frame layout of ``logistic_model``: coef = (X'X)^-1 X'y,
+    Sig_inv = X'X / sigma2 with sigma2 = RSS/(n-p) — R ``lm(y~x-1)`` + ``solve(vcov)`` (dlsa/R/wlse_func.R:169-182;
+    per-group OLS precedent projects/results/linear_regression_dc.py:27-39)."""
+    sample_df = sample_df.reset_index(drop=True)
+    X, y, names = _design(sample_df, Y_name, False, [], dummy_factors_baseline, [])
+    off = torch.tensor([0, X.shape[0]], dtype=torch.int64, device=X.device)
+    fits = engine.fit_linear_partitions(X, y, off)
+    if int(fits.status.item()) != 0:
+        raise ValueError("linear_model: X'X is not positive definite")
+    return _frame(fits.coef[0].cpu().numpy(), fits.Sig_invMcoef[0].cpu().numpy(), fits.Sig_inv[0].cpu().numpy(), names)

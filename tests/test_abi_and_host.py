@@ -1,0 +1,111 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/dlsa_b200.h declares (no compute calls),
+host-side layout logic against the reference goldens, and the no-CPU-fallback rule."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+HEADER = os.path.join(ROOT, "include", "dlsa_b200.h")
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dlsa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from dlsa_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 17
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT\s+(dlsa_[a-z0-9_]+)", out))
+    assert set(syms) <= exported, set(syms) - exported
+    assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)  # binding mirrors the header 1:1
+    assert _lib.lib.dlsa_abi_version() == 1
+    assert _lib.launch_count() >= 0
+    # size queries are pure host functions
+    assert _lib.lib.dlsa_irls_pass_workspace_bytes(1024, 50, 97657) == 0  # one CTA per partition: no partials
+    assert _lib.lib.dlsa_irls_pass_workspace_bytes(16, 20, 6250) > 0
+    assert _lib.lib.dlsa_lars_path_workspace_bytes(50, 400) >= 50 * 50 * 8
+
+
+def test_header_cites_the_reference_interfaces():
+    src = open(HEADER).read()
+    for cite in ["dlsa/models.py:110-113", "dlsa/models.py:114,130", "dlsa/R/wlse_func.R:55-62", "dlsa/dlsa.py:30-34",
+                 "dlsa/dlsa.py:48", "dlsa/lsa.py:90-212", "dlsa/models.py:151-225", "dlsa/models.py:6-40"]:
+        assert cite in src, cite
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    from dlsa_b200 import _lib
+    rc = _lib.lib.dlsa_irls_pass_f64(None, 4, None, None, 1, 4, 0, 0, None, None, None, None, None, 10, None, 0, None)
+    assert rc == -1 and b"null pointer" in _lib.lib.dlsa_last_error()
+    rc = _lib.lib.dlsa_lars_path_f64(None, None, 0, 0, 1.0, 0, 1e-16, 0, None, None, None, None, None, None, None, None, 0, None)
+    assert rc == -1
+    with pytest.raises(_lib.DlsaLibraryError):
+        _lib.check(rc, "lars")
+
+
+def test_no_cpu_fallback():
+    from dlsa_b200 import engine
+    X = torch.zeros(8, 3, dtype=torch.float64)
+    with pytest.raises(ValueError, match="no CPU path"):
+        engine.fit_logistic_partitions(X, torch.zeros(8, dtype=torch.float64), torch.tensor([0, 8]))
+    # the product never imports the oracle
+    for root, _, files in os.walk(os.path.join(ROOT, "dlsa_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_dummy_bookkeeping_matches_reference_golden():
+    from dlsa_b200 import dummies
+    g = load_golden("dummy_layout.npz")
+    df = pd.DataFrame({"Month": g["in_Month"], "Carrier": g["in_Carrier"]})
+    counts = dummies.dummy_factors_counts(df, ["Month", "Carrier"])
+    assert [str(k) for k in counts["Month"].keys()] == list(g["ref_count_keys_Month"])
+    assert list(counts["Carrier"].keys()) == list(g["ref_count_keys_Carrier"])
+    info = dummies.select_dummy_factors(counts, list(g["in_keep_top"]), "000_OTHERS")
+    assert info["factor_selected"]["Carrier"] == list(g["ref_selected_Carrier"])
+    assert info["factor_dropped"]["Carrier"] == list(g["ref_dropped_Carrier"])
+    assert info["factor_selected_names"]["Carrier"] == list(g["ref_selected_names_Carrier"])
+    assert info["factor_selected_names"]["Month"] == list(g["ref_selected_names_Month"])
+    cols = dummies.design_columns(["partition_id", "y", "znum", "anum", "Month", "Carrier"], "y", info,
+                                  list(g["in_baselines"]), True)
+    assert ["par_id", "coef", "Sig_invMcoef"] + cols == list(g["ref_frame_columns"])
+    schema = dummies.convert_schema(["znum", "anum", "Month", "Carrier"], info, True, list(g["in_baselines"]))
+    assert [n for n, _ in schema] == cols and all(t == "double" for _, t in schema)
+    merged = dummies.cumsum_dicts(counts, counts)
+    assert merged["Carrier"]["A"] == 2 * counts["Carrier"]["A"] and dummies.cumsum_dicts({}, counts) is counts
+
+
+def test_sdummies_level_rule():
+    """dlsa/sdummies.py:41-83 (Spark absent -> parity unpinned): keep while cum share <= keep_top OR count >= 10%."""
+    from dlsa_b200 import dummies
+    counts = {"Carrier": {"A": 50, "B": 20, "C": 12, "D": 10, "E": 5, "F": 3}}
+    info = dummies.select_sdummy_levels(counts, [0.8])
+    assert info["factor_selected"]["Carrier"] == ["A", "B", "C", "D"]  # D kept by the 10% rule (cum = 0.92 > 0.8)
+    assert sorted(info["factor_dropped"]["Carrier"]) == ["E", "F"]
+    assert info["factor_selected_names"]["Carrier"] == ["A", "B", "C", "D", "000_OTHERS"]
+    assert dummies.select_sdummy_levels(counts, [0.8], dropLast=True)["factor_selected_names"]["Carrier"][-1] == "D"
+
+
+def test_synth_host_restatement_is_deterministic():
+    from dlsa_b200 import synth
+    u = synth.host_uniform(7, np.arange(5, dtype=np.uint64)[:, None], np.arange(3, dtype=np.uint64)[None, :])
+    assert u.shape == (5, 3) and np.all((u >= 0) & (u < 1))
+    assert np.array_equal(u, synth.host_uniform(7, np.arange(5, dtype=np.uint64)[:, None], np.arange(3, dtype=np.uint64)[None, :]))
+    big = synth.host_uniform(1, np.arange(200000, dtype=np.uint64), np.uint64(0))
+    assert abs(big.mean() - 0.5) < 5e-3 and abs(big.var() - 1 / 12) < 2e-3
+    off = synth.equal_partition_offsets(100_000_000, 1024)
+    sizes = (off[1:] - off[:-1])
+    assert int(off[-1]) == 100_000_000 and int(sizes.max()) == 97657 and int(sizes.min()) == 97656
+    assert np.array_equal(synth.true_beta(50), np.r_[np.ones(20), np.zeros(30)])

@@ -1,0 +1,175 @@
+"""GPU tests of the reference-facing façade (dlsa.models / dlsa.dlsa / dlsa.lsa names) against the reference goldens."""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from conftest import games_data, load_golden, sim_data
+from oracle import numpy_dlsa as onp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def relfro(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def games_frame():
+    X, y, K, g = games_data()
+    df = pd.DataFrame(X, columns=[f"G{i}" for i in range(1, 11)])
+    df["label"] = y
+    df.insert(0, "partition_id", np.arange(len(df)) % K)
+    return df, K, g
+
+
+def test_reference_names_and_signatures():
+    import inspect
+    import dlsa
+    from dlsa.models import logistic_model, logistic_model_eval, simulate_logistic
+    from dlsa.dlsa import dlsa as dlsa_fn, dlsa_mapred, dlsa_mapreduce
+    from dlsa.lsa import lars_lsa
+    assert list(inspect.signature(logistic_model).parameters)[:6] == ["sample_df", "Y_name", "fit_intercept", "dummy_info",
+                                                                      "dummy_factors_baseline", "data_info"]
+    assert list(inspect.signature(dlsa_fn).parameters)[:4] == ["Sig_inv_", "beta_", "sample_size", "fit_intercept"]
+    assert list(inspect.signature(lars_lsa).parameters) == ["Sigma0", "b0", "intercept", "n", "type", "eps", "max_steps"]
+    assert inspect.signature(lars_lsa).parameters["type"].default == "lar"
+    assert dlsa_mapreduce is dlsa_mapred
+    assert list(inspect.signature(simulate_logistic).parameters)[:4] == ["sample_size", "p", "partition_method", "partition_num"]
+
+
+def test_logistic_model_frames_mapred_dlsa_games():
+    from dlsa.models import logistic_model
+    from dlsa.dlsa import dlsa as dlsa_fn, dlsa_mapred
+    from dlsa.lsa import lars_lsa
+    df, K, g = games_frame()
+    frames = [logistic_model(df[df.partition_id == k], "label") for k in range(K)]
+    for k, f in enumerate(frames):
+        assert list(f.columns) == list(g["ref_frame_columns"])
+        assert f.shape == (10, 13) and list(f["par_id"]) == list(range(10))
+        assert np.max(np.abs(f["coef"].to_numpy() - g["ref_coef"][k])) < 1e-8
+        assert relfro(f.iloc[:, 3:].to_numpy(), g["ref_Sig_inv"][k]) < 1e-9
+    mr = dlsa_mapred(pd.concat(frames, ignore_index=True))
+    assert list(mr.columns) == list(g["ref_mapred_columns"])
+    assert np.max(np.abs(mr["beta_byOLS"].to_numpy() - g["ref_beta_byOLS"])) < 1e-6
+    assert np.max(np.abs(mr["beta_byONESHOT"].to_numpy() - g["ref_beta_byONESHOT"])) < 1e-9
+    assert relfro(mr.iloc[:, 2:].to_numpy(), g["ref_Sig_inv_sum"]) < 1e-9
+    assert np.allclose(dlsa_mapred(frames).to_numpy(), mr.to_numpy())  # list-of-frames input
+
+    class FakeSpark:  # duck-typed Spark DataFrame (dlsa/dlsa.py:30-34,52)
+        def __init__(self, pdf, n):
+            self._pdf, self._n, self.rdd = pdf, n, self
+
+        def toPandas(self):
+            return self._pdf
+
+        def getNumPartitions(self):
+            return self._n
+    mr2 = dlsa_mapred(FakeSpark(pd.concat(frames, ignore_index=True), 10))
+    assert np.allclose(mr2["beta_byONESHOT"].to_numpy() * 2, mr["beta_byONESHOT"].to_numpy())
+    out = dlsa_fn(Sig_inv_=mr.iloc[:, 2:], beta_=mr["beta_byOLS"], sample_size=len(df), fit_intercept=False)
+    assert list(out.columns) == ["beta_byAIC", "beta_byBIC"]
+    ib, ia = int(np.argmin(g["ref_lar_BIC"])), int(np.argmin(g["ref_lar_AIC"]))
+    assert np.max(np.abs(out["beta_byBIC"].to_numpy() - g["ref_lar_beta"][ib])) < 1e-8
+    assert np.max(np.abs(out["beta_byAIC"].to_numpy() - g["ref_lar_beta"][ia])) < 1e-8
+    assert np.array_equal(out["beta_byBIC"].to_numpy() != 0, g["ref_lar_beta"][ib] != 0)
+    fit = lars_lsa(np.matrix(mr.iloc[:, 2:].to_numpy()), mr["beta_byOLS"].to_numpy(), False, len(df), type="lasso")
+    assert set(fit) == {"AIC", "BIC", "beta", "beta0"}
+    assert np.allclose(fit["BIC"], g["ref_lasso_BIC"], rtol=1e-8, atol=1e-6)
+
+
+def test_partitions_batched_map_equals_per_partition_calls():
+    from dlsa.models import logistic_model, logistic_model_partitions
+    g = load_golden("sim_small_n6000_p7_k3.npz")
+    pid, y, X, K = sim_data(g)
+    df = pd.DataFrame(np.concatenate([pid[:, None].astype(float), y[:, None], X], axis=1),
+                      columns=["partition_id", "label"] + [f"x{i}" for i in range(X.shape[1])])
+    stacked = logistic_model_partitions(df, "label")
+    assert list(stacked.columns) == list(g["ref_frame_columns"])
+    for k in range(K):
+        one = logistic_model(df[df.partition_id == k], "label")
+        blk = stacked.iloc[k * 7:(k + 1) * 7]
+        assert np.allclose(blk.to_numpy(), one.to_numpy(), rtol=1e-12, atol=1e-12)
+        assert np.max(np.abs(blk["coef"].to_numpy() - g["ref_coef"][k])) < 1e-8
+
+
+def test_dummy_layout_and_zero_frame_match_reference():
+    from dlsa.models import logistic_model
+    from dlsa import dummies
+    g = load_golden("dummy_layout.npz")
+    df = pd.DataFrame({"partition_id": 0.0, "y": g["in_y"], "znum": g["in_znum"], "anum": g["in_anum"],
+                       "Month": g["in_Month"], "Carrier": g["in_Carrier"]})
+    info = dummies.select_dummy_factors(dummies.dummy_factors_counts(df, ["Month", "Carrier"]), list(g["in_keep_top"]))
+    base = list(g["in_baselines"])
+    frame = logistic_model(df, "y", fit_intercept=True, dummy_info=info, dummy_factors_baseline=base)
+    assert list(frame.columns) == list(g["ref_frame_columns"])  # bit-exact layout
+    ref = g["ref_frame"]
+    got = frame.to_numpy(dtype=float)
+    assert got.shape == (17, 20) and np.array_equal(got[:, 0], ref[:, 0])
+    assert np.max(np.abs(got[:, 1] - ref[:, 1])) < 1e-7
+    assert relfro(got[:, 3:], ref[:, 3:]) < 1e-9
+    with pytest.warns(UserWarning, match="Dummies:"):
+        zero = logistic_model(df[df["Month"] != 7], "y", fit_intercept=True, dummy_info=info, dummy_factors_baseline=base)
+    assert list(zero.columns) == list(g["ref_zero_frame_columns"])
+    assert np.array_equal(zero.to_numpy(dtype=float), g["ref_zero_frame"])
+    # standardisation with describe()-style data_info (rows 1, 2 = mean, std; dlsa/models.py:99-101)
+    desc = df[["anum", "znum"]].describe()
+    data_info = {c: desc[c].to_numpy() for c in ["anum", "znum"]}
+    fs = logistic_model(df, "y", fit_intercept=True, dummy_info=info, dummy_factors_baseline=base, data_info=data_info)
+    ref_s = onp.logistic_model_frame(df, "y", fit_intercept=True, dummy_info=info, dummy_factors_baseline=base,
+                                     data_info=data_info)
+    assert np.max(np.abs(fs["coef"].to_numpy() - ref_s["coef"].to_numpy())) < 1e-8
+    assert relfro(fs.iloc[:, 3:].to_numpy(), ref_s.iloc[:, 3:].to_numpy()) < 1e-9
+
+
+def test_intercept_dlsa_follows_r_spec():
+    from dlsa.dlsa import dlsa as dlsa_fn
+    g = load_golden("sim_icpt_n20000_p12_k4.npz")
+    S, th, n = g["ref_Sig_inv_sum"], g["ref_beta_byOLS"], int(g["in_n"])
+    out = dlsa_fn(pd.DataFrame(S), pd.Series(th), n, fit_intercept=True)
+    bA, bB, _ = onp.dlsa_select(S, th, n, fit_intercept=True)
+    assert out.shape == (13, 2)
+    assert np.max(np.abs(out["beta_byAIC"].to_numpy() - bA)) < 1e-9
+    assert np.max(np.abs(out["beta_byBIC"].to_numpy() - bB)) < 1e-9
+
+
+def test_model_eval_and_simulate_and_linear():
+    from dlsa.models import logistic_model_eval, simulate_logistic, linear_model
+    from dlsa.model_eval import logistic_model_eval_sdf
+    df, K, g = games_frame()
+    par = pd.DataFrame({"beta_byOLS": g["ref_beta_byOLS"], "beta_byONESHOT": g["ref_beta_byONESHOT"],
+                        "beta_byBIC": g["ref_lar_beta"][9]})
+    X, y = df.iloc[:, 1:11].to_numpy(), df["label"].to_numpy()
+    ref = onp.logistic_loglik(X, y, par.to_numpy())
+    one = logistic_model_eval(df, "label", par)
+    assert list(one.columns) == list(par.columns) and np.allclose(one.to_numpy()[0], ref, rtol=1e-10)
+    tot = logistic_model_eval_sdf(df, par, False, "label", [], [], [])
+    assert np.allclose(tot.to_numpy()[0], ref, rtol=1e-10)
+    sim = simulate_logistic(20000, 10, "systematic", 4, seed=3)
+    assert list(sim.columns) == ["partition_id", "label"] + [f"x{i}" for i in range(10)]
+    assert sim.shape == (20000, 12) and set(np.unique(sim["label"])) == {0.0, 1.0}
+    assert np.array_equal(sim["partition_id"].to_numpy(), np.arange(20000) % 4)
+    assert abs(sim.iloc[:, 2:].to_numpy().mean()) < 5e-3 and sim.iloc[:, 2:].to_numpy().min() >= -0.5
+    with pytest.raises(Exception, match="No such partition method"):
+        simulate_logistic(10, 2, "random", 2)
+    rng = np.random.default_rng(0)
+    Xl = rng.standard_normal((4000, 6))
+    yl = Xl @ np.array([3, 1.5, 0, 0, 2, 0.0]) + rng.standard_normal(4000)
+    dfl = pd.DataFrame(Xl, columns=[f"x{i}" for i in range(6)])
+    dfl["yy"] = yl
+    dfl.insert(0, "partition_id", 0)
+    fl = linear_model(dfl, "yy")
+    th, Sg, Sgt, _ = onp.ols_fit(Xl, yl)
+    assert np.max(np.abs(fl["coef"].to_numpy() - th)) < 1e-10 and relfro(fl.iloc[:, 3:].to_numpy(), Sg) < 1e-11
+
+
+def test_single_class_partition_raises_like_sklearn():
+    from dlsa.models import logistic_model
+    df = pd.DataFrame({"partition_id": 0, "label": 1.0, "x0": [1.0, 2.0, 3.0, 4.0], "x1": [0.2, -0.1, 0.3, 0.0]})
+    with pytest.raises(ValueError):
+        logistic_model(df, "label", config=__import__("dlsa_b200").EngineConfig(max_iter=10))
