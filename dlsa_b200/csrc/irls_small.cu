@@ -1,16 +1,22 @@
-// K1 (p <= 56): fused Newton/IRLS pass, one warp owns the whole lower-triangular Gram.
+// K1 (p <= 56): fused Newton/IRLS pass, warp-specialised.
 //
 // Reference arithmetic replaced (per partition): eta = X beta, prob = sigmoid(eta), w = prob(1-prob),
 // g = X'(y-prob), H = X' diag(w) X  — dlsa/R/wlse_func.R:47-54, dlsa/models.py:114,130.
 //
-// Design: CTA = 8 independent warps on one partition slice.  Each warp streams its own
-// 32-row (or 16-row) chunks of X through a private multi-stage ring in shared memory, filled by TMA 1-D
-// bulk copies (one 8*px-byte copy per row into a padded row, stride == 4 mod 8 doubles, so every DMMA
-// fragment load is bank-conflict free) and signalled on per-stage mbarriers.  Per chunk: eta by DFMA on a
-// (row, column-quarter) lane grid, sigmoid/weights one row per lane, then H += (wX)'X on FP64 tensor cores
-// (DMMA.8x8x4) with all NT(NT+1)/2 lower-triangle 8x8 accumulator tiles held in that warp's registers.
-// X is read from HBM exactly once per pass.  The 8 warps' accumulators are summed in a fixed order through
-// shared memory, so results are bitwise reproducible for a given launch configuration.
+// Design.  FP64 DMMA and DFMA share one 64 FMA/clk/SM pipe on B200, so the pass is bound by
+// that pipe; the kernel is built so the pipe never waits for anything else:
+//   * CTA = 16 warps.  Warps 0..7 are MMA warps: each owns a private ring of 32-row chunks of X and keeps ALL
+//     NT(NT+1)/2 lower-triangle 8x8 accumulator tiles of H in registers (setmaxnreg raises them to 184 regs);
+//     their inner loop is only LDS + DMUL + DMMA.8x8x4 (+ 1 DFMA per fragment for g).
+//   * Warps 8..15 are row warps (72 regs; the highest warp ids, which the issue arbiter prefers, so their few
+//     FP64 instructions do not queue behind the MMA warps).  Row warp r feeds MMA warp r: it issues the
+//     TMA bulk copies (4 per chunk), computes eta (DFMA on a conflict-free lane grid), the sigmoid, the weights
+//     w and residuals r one chunk ahead, and hands them over through shared memory + mbarriers.  The long
+//     dependent FP64 chains (exp, divide) therefore overlap the other warps' DMMAs instead of stalling them.
+//   * Chunk layout in shared memory: 4 groups of CH/4 dense rows (one bulk copy each), groups 4 doubles apart
+//     modulo 16, so that the 4 rows of a DMMA k-step (one per group) and the 4x4 lane grid of the eta stage hit
+//     16 distinct 8-byte banks for every even px.
+//   * X is read from HBM exactly once per pass; the 8 MMA warps' accumulators are summed in a fixed order.
 #include "common.cuh"
 
 namespace dlsa {
@@ -25,18 +31,31 @@ struct IrlsArgs {
     double* outH;   // [K*S][p*p]   (S == 1: the caller's H)
     double* outg;   // [K*S][p]
     double* outll;  // [K*S] or nullptr
-    int K, px, p, icpt, S, Sd, aligned, want_ll;
+    int K, px, p, icpt, S, aligned, want_ll;
 };
 
-constexpr int kWarps = 8;
+constexpr int kMmaWarps = 8;
+constexpr int kRowWarps = 8;
+constexpr int kThreads = (kMmaWarps + kRowWarps) * 32;
+constexpr int kRegsRow = 72;
+constexpr int kRegsMma = 184;  // 72*256 + 184*256 = 65536 = 128*512
 
-template <int NT>
-__device__ __forceinline__ constexpr int tri_index(int i, int j) { return i * (i + 1) / 2 + j; }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 template <int NT, int CH, int STAGES, int FAMILY>
-__global__ void __launch_bounds__(kWarps * 32, 1) irls_small_kernel(const IrlsArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) irls_small_kernel(const IrlsArgs a) {
     constexpr int NTRI = NT * (NT + 1) / 2;
-    constexpr int NG = CH / 8;  // 8-row groups per chunk
+    constexpr int GR = CH / 4;   // rows per group (= k-steps per chunk)
+    constexpr int NG = CH / 8;   // 8-row groups of the eta stage
     constexpr int NRED = NTRI * 64 + NT * 8 + 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
@@ -45,29 +64,28 @@ __global__ void __launch_bounds__(kWarps * 32, 1) irls_small_kernel(const IrlsAr
     const int k = blockIdx.x / a.S, slice = blockIdx.x % a.S;
     if (a.active != nullptr && a.active[k] == 0) return;
 
+    const int p = a.p, px = a.px;
     const int64_t row_lo = a.part_off[k];
     const int64_t n_k = a.part_off[k + 1] - row_lo;
     const int64_t nchunks = (n_k + CH - 1) / CH;
     const int64_t cps = (nchunks + a.S - 1) / a.S;
     const int64_t c_lo = (int64_t)slice * cps;
     const int64_t c_hi = (c_lo + cps < nchunks) ? (c_lo + cps) : nchunks;
-    // this warp's chunks: c_lo + warp + i*kWarps, i = 0..my_n-1
-    const int64_t first = c_lo + warp;
-    const int my_n = (first < c_hi) ? (int)((c_hi - first + kWarps - 1) / kWarps) : 0;
 
-    const int Sd = a.Sd, p = a.p, px = a.px;
-    const int stage_doubles = CH * Sd;
-    double* tiles = reinterpret_cast<double*>(smem_raw);
-    double* my_tiles = tiles + (size_t)warp * STAGES * stage_doubles;
-    size_t off = (size_t)kWarps * STAGES * stage_doubles;
-    double* ws = tiles + off + (size_t)warp * CH * 2;
-    double* rs = ws + CH;
-    off += (size_t)kWarps * CH * 2;
-    double* beta_s = tiles + off;
+    // ---- shared memory carve-up -------------------------------------------------------------------
+    const int S = px + (px & 1);          // dense row stride (even); odd px only on the cp.async path
+    const int gstride = GR * S + 4;       // doubles between row groups: == 4 (mod 16) apart for even S
+    const int stage_doubles = 4 * gstride;
+    double* ring = reinterpret_cast<double*>(smem_raw);                      // [8][STAGES][stage_doubles]
+    size_t off = (size_t)kMmaWarps * STAGES * stage_doubles;
+    double* wr_all = ring + off;                                             // [8][STAGES][2*CH]
+    off += (size_t)kMmaWarps * STAGES * 2 * CH;
+    double* beta_s = ring + off;                                             // [NT*8]
     off += NT * 8;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + off) + warp * STAGES;
+    double* ll_s = ring + off;                                               // [kRowWarps]
+    off += 8;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + off);                // [8][STAGES][3]: x_full, wr_full, empty
 
-    // ---- one-time setup ------------------------------------------------------------------------
     if (threadIdx.x < NT * 8) {
         const int c = threadIdx.x;  // internal column: features 0..px-1, then the intercept
         double bv = 0.0;
@@ -77,186 +95,251 @@ __global__ void __launch_bounds__(kWarps * 32, 1) irls_small_kernel(const IrlsAr
         }
         beta_s[c] = bv;
     }
-    if (a.icpt) {
-        for (int r = lane; r < STAGES * CH; r += 32) my_tiles[(size_t)r * Sd + px] = 1.0;
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; s++) mbar_init(smem_u32(&bars[s]), a.aligned ? 1u : 32u);
+    // zero the ring once: tail chunks leave stale finite rows behind, never uninitialised ones
+    for (int e = threadIdx.x; e < kMmaWarps * STAGES * stage_doubles; e += kThreads) ring[e] = 0.0;
+    if (threadIdx.x < kMmaWarps * STAGES) {
+        uint64_t* b = bars + threadIdx.x * 3;
+        mbar_init(smem_u32(&b[0]), a.aligned ? 1u : 32u);
+        mbar_init(smem_u32(&b[1]), 1u);
+        mbar_init(smem_u32(&b[2]), 1u);
         fence_mbar_init();
     }
     fence_proxy_async();
     __syncthreads();
 
-    const double* Xp = a.X + row_lo * a.ldx;
-    const double* yp = a.y + row_lo;
-    const uint32_t row_bytes = (uint32_t)px * 8u;
-
-    auto issue = [&](int ci) {
-        if (ci >= my_n) return;
-        const int st = ci % STAGES;
-        const int64_t r0 = (first + (int64_t)ci * kWarps) * CH;
-        const int valid = (n_k - r0 < CH) ? (int)(n_k - r0) : CH;
-        const uint32_t bar = smem_u32(&bars[st]);
-        double* dst = my_tiles + (size_t)st * stage_doubles;
-        if (a.aligned) {
-            if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * CH);
-            __syncwarp();
-            if (lane < CH) {
-                const int rr = lane < valid ? lane : valid - 1;  // tail rows re-read a valid row; their weight is 0
-                bulk_g2s(smem_u32(dst + (size_t)lane * Sd), Xp + (r0 + rr) * a.ldx, row_bytes, bar);
-            }
-        } else {
-            for (int e = lane; e < CH * px; e += 32) {
-                const int row = e / px, col = e - row * px;
-                const int rr = row < valid ? row : valid - 1;
-                cp_async8(smem_u32(dst + (size_t)row * Sd + col), Xp + (r0 + rr) * a.ldx + col);
-            }
-            cp_async_mbar_arrive_noinc(bar);
+    if (warp >= kMmaWarps) {
+        // =========================== row warp: TMA producer + eta / sigmoid / weights ==================
+        setmaxnreg_dec<kRegsRow>();
+        const int rw = warp - kMmaWarps;  // row warp index 0..7; serves MMA warp rw (same sub-partition)
+        const double* Xp = a.X + row_lo * a.ldx;
+        const double* yp = a.y + row_lo;
+        constexpr int NU = 1;
+        int64_t first[NU];
+        int my_n[NU];
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+            const int m = rw + 4 * u;  // MMA warp index served
+            first[u] = c_lo + m;
+            my_n[u] = (first[u] < c_hi) ? (int)((c_hi - first[u] + kMmaWarps - 1) / kMmaWarps) : 0;
         }
-    };
-    // row this lane owns in the per-row (sigmoid) stage: rho = 8*q + a8 when q < NG
-    const int rho = 8 * q + a8;
-    auto load_y = [&](int ci) -> double {
-        if (ci >= my_n || q >= NG) return 0.0;
-        const int64_t r = (first + (int64_t)ci * kWarps) * CH + rho;
-        return (r < n_k) ? __ldg(yp + r) : 0.0;
-    };
+        const int n_iter = my_n[0];
 
-    double C[NTRI][2];
-    double gacc[NT];
-#pragma unroll
-    for (int t = 0; t < NTRI; t++) C[t][0] = C[t][1] = 0.0;
-#pragma unroll
-    for (int t = 0; t < NT; t++) gacc[t] = 0.0;
-    double llacc = 0.0;
+        auto issue = [&](int u, int ci) {
+            const int m = rw + 4 * u;
+            const int st = ci % STAGES;
+            const int64_t r0 = (first[u] + (int64_t)ci * kMmaWarps) * CH;
+            const int valid = (n_k - r0 < CH) ? (int)(n_k - r0) : CH;
+            const uint32_t bar = smem_u32(&bars[(m * STAGES + st) * 3 + 0]);
+            double* dst = ring + (size_t)(m * STAGES + st) * stage_doubles;
+            if (a.aligned) {
+                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * (uint32_t)px * 8u);
+                __syncwarp();
+                if (lane < 4) {
+                    const int rows = valid - lane * GR < GR ? valid - lane * GR : GR;
+                    if (rows > 0)
+                        bulk_g2s(smem_u32(dst + (size_t)lane * gstride), Xp + (r0 + lane * GR) * a.ldx,
+                                 (uint32_t)rows * (uint32_t)px * 8u, bar);
+                }
+            } else {
+                for (int e = lane; e < valid * px; e += 32) {
+                    const int row = e / px, col = e - row * px;
+                    cp_async8(smem_u32(dst + (size_t)(row / GR) * gstride + (size_t)(row % GR) * S + col),
+                              Xp + (r0 + row) * a.ldx + col);
+                }
+                cp_async_mbar_arrive_noinc(bar);
+            }
+        };
+        // eta-stage row of this lane in 8-row group g: one row from each of the 4 copy groups per half-warp
+        // row(g, a8) = GR*(a8&3) + 2g + (a8>>2)  (GR = 8: CH = 32;  GR = 4: CH = 16)
+        const int erow_base = (a8 & 3) * gstride + (a8 >> 2) * S;   // + 2g*S
+        const int erow_idx = GR * (a8 & 3) + (a8 >> 2);             // + 2g
+        auto load_y = [&](int u, int ci) -> double {
+            if (ci >= my_n[u] || q >= NG) return 0.0;
+            const int64_t r = (first[u] + (int64_t)ci * kMmaWarps) * CH + erow_idx + 2 * q;
+            return (r < n_k) ? __ldg(yp + r) : 0.0;
+        };
 
-    // column masks of the last (ragged) 8-column tile
-    const bool ok_last = (8 * (NT - 1) + a8) < p;
-    const int col_last = ok_last ? 8 * (NT - 1) + a8 : 0;
+        const bool dense_ok = a.aligned && (a.ldx == px);
+        (void)dense_ok;
+#pragma unroll
+        for (int u = 0; u < NU; u++)
+            for (int s = 0; s < STAGES; s++)
+                if (s < my_n[u]) issue(u, s);
+        double y_next[NU] = {load_y(0, 0)};
+        double llacc = 0.0;
 
+        for (int ci = 0; ci < n_iter; ci++) {
+            const int st = ci % STAGES;
+            const uint32_t par = (uint32_t)((ci / STAGES) & 1);
+            double y_cur[NU] = {y_next[0]};
+            y_next[0] = load_y(0, ci + 1);
 #pragma unroll
-    for (int s = 0; s < STAGES; s++) issue(s);
-    double y_next = load_y(0);
-
-    for (int ci = 0; ci < my_n; ci++) {
-        const int st = ci % STAGES;
-        const double y_cur = y_next;
-        y_next = load_y(ci + 1);
-        const int64_t r0 = (first + (int64_t)ci * kWarps) * CH;
-        const int valid = (n_k - r0 < CH) ? (int)(n_k - r0) : CH;
-        mbar_wait(smem_u32(&bars[st]), (uint32_t)((ci / STAGES) & 1));
-        const double* T = my_tiles + (size_t)st * stage_doubles;
-
-        // ---- eta = x . beta on a (row = 8g + a8, column quarter q) lane grid ---------------------
-        double wv_row = 0.0, rv_row = 0.0;
-        if (FAMILY == DLSA_FAMILY_LOGISTIC) {
-            double s[NG];
+            for (int u = 0; u < NU; u++) {
+                if (ci < my_n[u]) {
+                    const int m = rw + 4 * u;
+                    const int64_t r0 = (first[u] + (int64_t)ci * kMmaWarps) * CH;
+                    const int valid = (n_k - r0 < CH) ? (int)(n_k - r0) : CH;
+                    uint64_t* b = bars + (m * STAGES + st) * 3;
+                    const double* T = ring + (size_t)(m * STAGES + st) * stage_doubles;
+                    double* ws = wr_all + (size_t)(m * STAGES + st) * 2 * CH;
+                    double* rs = ws + CH;
+                    double wv = 0.0, rv = 0.0;
+                    const int rho = erow_idx + 2 * q;  // row owned in the per-row stage (when q < NG)
+                    const bool rowvalid = (q < NG) && (rho < valid);
+                    if (FAMILY == DLSA_FAMILY_LOGISTIC) {
+                        mbar_wait(smem_u32(&b[0]), par);
+                        double s[NG];
 #pragma unroll
-            for (int g = 0; g < NG; g++) s[g] = 0.0;
+                        for (int g = 0; g < NG; g++) s[g] = 0.0;
 #pragma unroll
-            for (int t = 0; t < 2 * NT; t++) {
-                const int col = 4 * t + q;
-                const bool ok = (t < 2 * NT - 2) || (col < p);
-                const int colc = ok ? col : 0;
-                const double bv = beta_s[col];
+                        for (int t = 0; t < 2 * NT; t++) {
+                            const int col = 4 * t + q;
+                            const bool in_x = (t < 2 * NT - 2) || (col < px);
+                            const bool is_one = (t >= 2 * NT - 2) && (col == px) && a.icpt;
+                            const int colc = in_x ? col : 0;
+                            const double bv = beta_s[col];
 #pragma unroll
-                for (int g = 0; g < NG; g++) {
-                    double xv = T[(size_t)(8 * g + a8) * Sd + colc];
-                    xv = ok ? xv : 0.0;
-                    s[g] = fma(xv, bv, s[g]);
+                            for (int g = 0; g < NG; g++) {
+                                double xv = T[erow_base + 2 * g * S + colc];
+                                xv = in_x ? xv : (is_one ? 1.0 : 0.0);
+                                s[g] = fma(xv, bv, s[g]);
+                            }
+                        }
+                        double eta = 0.0;
+#pragma unroll
+                        for (int g = 0; g < NG; g++) {
+                            s[g] += shfl_xor_f64(s[g], 1);
+                            s[g] += shfl_xor_f64(s[g], 2);
+                            eta = (q == g) ? s[g] : eta;
+                        }
+                        const double pr = sigmoid_f64(eta);
+                        wv = pr * (1.0 - pr);
+                        rv = y_cur[u] - pr;
+                        if (a.want_ll && rowvalid) llacc += y_cur[u] * eta - log1pexp_f64(eta);
+                    } else {
+                        wv = 1.0;
+                        rv = y_cur[u];
+                        if (rowvalid) llacc = fma(y_cur[u], y_cur[u], llacc);
+                    }
+                    if (q < NG) {
+                        ws[rho] = rowvalid ? wv : 0.0;
+                        rs[rho] = rowvalid ? rv : 0.0;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&b[1]));  // w/r of this chunk are ready
                 }
             }
-            double eta = 0.0;
+            // refill the stage the MMA warp finished last (chunk ci-1) with chunk ci-1+STAGES
+            if (ci >= 1) {
 #pragma unroll
-            for (int g = 0; g < NG; g++) {
-                s[g] += shfl_xor_f64(s[g], 1);
-                s[g] += shfl_xor_f64(s[g], 2);
-                eta = (q == g) ? s[g] : eta;
+                for (int u = 0; u < NU; u++) {
+                    const int cn = ci - 1 + STAGES;
+                    if (cn < my_n[u]) {
+                        const int m = rw + 4 * u;
+                        const int stp = (ci - 1) % STAGES;
+                        mbar_wait(smem_u32(&bars[(m * STAGES + stp) * 3 + 2]), (uint32_t)(((ci - 1) / STAGES) & 1));
+                        fence_proxy_async();
+                        issue(u, cn);
+                    }
+                }
             }
-            const double pr = sigmoid_f64(eta);
-            wv_row = pr * (1.0 - pr);
-            rv_row = y_cur - pr;
-            if (a.want_ll && q < NG && rho < valid) llacc += y_cur * eta - log1pexp_f64(eta);
-        } else {
-            wv_row = 1.0;
-            rv_row = y_cur;
-            if (q < NG && rho < valid) llacc = fma(y_cur, y_cur, llacc);
         }
-        if (q < NG) {
-            const bool rowvalid = rho < valid;
-            ws[rho] = rowvalid ? wv_row : 0.0;
-            rs[rho] = rowvalid ? rv_row : 0.0;
-        }
-        __syncwarp();
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) llacc += shfl_xor_f64(llacc, m);
+        if (lane == 0) ll_s[rw] = llacc;
+        named_bar_sync(1, kThreads);  // (A) every warp is done with the ring
+        named_bar_sync(2, kThreads);  // (B) partial accumulators are in shared memory
+    } else {
+        // =========================== MMA warp: H += (wX)'X on DMMA, g += X'r ===========================
+        setmaxnreg_inc<kRegsMma>();
+        const int m = warp;
+        const int64_t first = c_lo + m;
+        const int my_n = (first < c_hi) ? (int)((c_hi - first + kMmaWarps - 1) / kMmaWarps) : 0;
 
-        // ---- H += (wX)'X on DMMA, g += X'r on DFMA ----------------------------------------------
+        double C[NTRI][2];
+        double gacc[NT];
+#pragma unroll
+        for (int t = 0; t < NTRI; t++) C[t][0] = C[t][1] = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; t++) gacc[t] = 0.0;
+
+        // fragment element of this lane in k-step ks: row = GR*q + ks (group q), column 8t + a8
+        const int frag_base = q * gstride;  // + ks*S + 8t + a8
+        const int col_last = 8 * (NT - 1) + a8;
+        const bool last_in_x = col_last < px;
+        const double last_const = (col_last == px && a.icpt) ? 1.0 : 0.0;
+        const int col_last_c = last_in_x ? col_last : 0;
+
+        for (int ci = 0; ci < my_n; ci++) {
+            const int st = ci % STAGES;
+            const uint32_t par = (uint32_t)((ci / STAGES) & 1);
+            uint64_t* b = bars + (m * STAGES + st) * 3;
+            const double* T = ring + (size_t)(m * STAGES + st) * stage_doubles + frag_base;
+            const double* ws = wr_all + (size_t)(m * STAGES + st) * 2 * CH;
+            const double* rs = ws + CH;
+            mbar_wait(smem_u32(&b[0]), par);  // X chunk landed (async-proxy writes visible to this warp)
+            mbar_wait(smem_u32(&b[1]), par);  // weights / residuals written by the row warp
 #pragma unroll 2
-        for (int s4 = 0; s4 < CH / 4; s4++) {
-            const int row = 4 * s4 + q;
-            const double wv = ws[row], rv = rs[row];
-            const double* Tr = T + (size_t)row * Sd;
-            double f[NT], av[NT];
+            for (int ks = 0; ks < GR; ks++) {
+                const int row = GR * q + ks;
+                const double wv = ws[row], rv = rs[row];
+                const double* Tr = T + ks * S;
+                double f[NT], av[NT];
 #pragma unroll
-            for (int t = 0; t < NT - 1; t++) f[t] = Tr[8 * t + a8];
-            {
-                const double v = Tr[col_last];
-                f[NT - 1] = ok_last ? v : 0.0;
+                for (int t = 0; t < NT - 1; t++) f[t] = Tr[8 * t + a8];
+                {
+                    const double v = Tr[col_last_c];
+                    f[NT - 1] = last_in_x ? v : last_const;
+                }
+#pragma unroll
+                for (int t = 0; t < NT; t++) {
+                    av[t] = wv * f[t];
+                    gacc[t] = fma(rv, f[t], gacc[t]);
+                }
+#pragma unroll
+                for (int i = 0; i < NT; i++)
+#pragma unroll
+                    for (int j = 0; j <= i; j++)
+                        dmma884(C[i * (i + 1) / 2 + j][0], C[i * (i + 1) / 2 + j][1], av[i], f[j]);
             }
-#pragma unroll
-            for (int t = 0; t < NT; t++) {
-                av[t] = wv * f[t];
-                gacc[t] = fma(rv, f[t], gacc[t]);
-            }
-#pragma unroll
-            for (int i = 0; i < NT; i++)
-#pragma unroll
-                for (int j = 0; j <= i; j++) dmma884(C[i * (i + 1) / 2 + j][0], C[i * (i + 1) / 2 + j][1], av[i], f[j]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&b[2]));  // stage free
         }
-        __syncwarp();
-        // refill this stage with the chunk STAGES ahead (generic reads above -> async writes: proxy fence)
-        if (ci + STAGES < my_n) {
-            fence_proxy_async();
-            issue(ci + STAGES);
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            gacc[t] += shfl_xor_f64(gacc[t], 1);
+            gacc[t] += shfl_xor_f64(gacc[t], 2);
         }
+        named_bar_sync(1, kThreads);  // (A) every warp is done with the ring: reuse it as the reduction buffer
+        double* red = ring + (size_t)m * NRED;
+#pragma unroll
+        for (int t = 0; t < NTRI; t++) {
+            red[t * 64 + a8 * 8 + 2 * q] = C[t][0];
+            red[t * 64 + a8 * 8 + 2 * q + 1] = C[t][1];
+        }
+        if (q == 0) {
+#pragma unroll
+            for (int t = 0; t < NT; t++) red[NTRI * 64 + 8 * t + a8] = gacc[t];
+        }
+        named_bar_sync(2, kThreads);  // (B)
     }
 
-    // ---- CTA reduction in a fixed order, then emit ------------------------------------------------
-#pragma unroll
-    for (int t = 0; t < NT; t++) {
-        gacc[t] += shfl_xor_f64(gacc[t], 1);
-        gacc[t] += shfl_xor_f64(gacc[t], 2);
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) llacc += shfl_xor_f64(llacc, m);
-
-    __syncthreads();  // every warp is done with its tiles; reuse them as the reduction buffer
-    double* red = tiles + (size_t)warp * NRED;
-#pragma unroll
-    for (int t = 0; t < NTRI; t++) {
-        red[t * 64 + a8 * 8 + 2 * q] = C[t][0];
-        red[t * 64 + a8 * 8 + 2 * q + 1] = C[t][1];
-    }
-    if (q == 0) {
-#pragma unroll
-        for (int t = 0; t < NT; t++) red[NTRI * 64 + 8 * t + a8] = gacc[t];
-    }
-    if (lane == 0) red[NTRI * 64 + NT * 8] = llacc;
-    __syncthreads();
-
+    // ---- fixed-order reduction over the 8 MMA warps, then emit (all 12 warps) ------------------------
     double* oH = a.outH + (size_t)blockIdx.x * p * p;
     double* og = a.outg + (size_t)blockIdx.x * p;
-    for (int e = threadIdx.x; e < NTRI * 64 + NT * 8 + 1; e += kWarps * 32) {
+    for (int e = threadIdx.x; e < NTRI * 64 + NT * 8 + 1; e += kThreads) {
         double v = 0.0;
+        if (e < NTRI * 64 + NT * 8) {
 #pragma unroll
-        for (int w = 0; w < kWarps; w++) v += tiles[(size_t)w * NRED + e];
+            for (int w = 0; w < kMmaWarps; w++) v += ring[(size_t)w * NRED + e];
+        }
         if (e < NTRI * 64) {
-            const int tt = e >> 6, m = (e >> 3) & 7, n = e & 7;
+            const int tt = e >> 6, mm = (e >> 3) & 7, nn = e & 7;
             int i = 0;
             while ((i + 1) * (i + 2) / 2 <= tt) i++;
             const int j = tt - i * (i + 1) / 2;
-            const int r_ = 8 * i + m, c_ = 8 * j + n;
-            if (r_ < p && c_ < p && (i != j || n <= m)) {
+            const int r_ = 8 * i + mm, c_ = 8 * j + nn;
+            if (r_ < p && c_ < p && (i != j || nn <= mm)) {
                 const int ro = a.icpt ? (r_ == px ? 0 : r_ + 1) : r_;
                 const int co = a.icpt ? (c_ == px ? 0 : c_ + 1) : c_;
                 oH[(size_t)ro * p + co] = v;
@@ -269,7 +352,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) irls_small_kernel(const IrlsAr
                 og[co] = v;
             }
         } else if (a.outll != nullptr) {
-            a.outll[blockIdx.x] = v;
+            a.outll[blockIdx.x] = (((ll_s[0] + ll_s[1]) + (ll_s[2] + ll_s[3])) + ((ll_s[4] + ll_s[5]) + (ll_s[6] + ll_s[7])));
         }
     }
 }
@@ -297,35 +380,32 @@ __global__ void slice_reduce_kernel(const double* __restrict__ pH, const double*
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-static int row_stride_doubles(int p) {
-    int s = p;
-    while (s % 8 != 4) s++;
-    return s;
-}
-
 struct SmallCfg {
-    int NT, CH, STAGES, Sd;
+    int NT, CH, STAGES;
     size_t smem;
 };
 
-static SmallCfg small_cfg(int p) {
+static SmallCfg small_cfg(int px, int p) {
     SmallCfg c;
     c.NT = (p + 7) / 8;
-    c.Sd = row_stride_doubles(p);
+    const int S = px + (px & 1);
     if (c.NT <= 4) { c.CH = 32; c.STAGES = 3; }
-    else if (c.Sd <= 52) { c.CH = 32; c.STAGES = 2; }
+    else if (S <= 52) { c.CH = 32; c.STAGES = 2; }
     else { c.CH = 16; c.STAGES = 3; }
-    c.smem = ((size_t)kWarps * c.STAGES * c.CH * c.Sd + (size_t)kWarps * c.CH * 2 + c.NT * 8) * 8 + kWarps * c.STAGES * 8 + 64;
+    const int gstride = (c.CH / 4) * S + 4;
+    c.smem = ((size_t)kMmaWarps * c.STAGES * 4 * gstride + (size_t)kMmaWarps * c.STAGES * 2 * c.CH + c.NT * 8 + 8) * 8 +
+             (size_t)kMmaWarps * c.STAGES * 3 * 8 + 128;
     return c;
 }
 
 int irls_small_slices(int K, int p, int64_t max_part_rows) {
-    SmallCfg c = small_cfg(p);
-    int64_t chunks = (max_part_rows + c.CH - 1) / c.CH;
+    const int CH = 32;
+    int64_t chunks = (max_part_rows + CH - 1) / CH;
     int64_t s_want = (148 * 4 + K - 1) / K;
-    int64_t s_max = chunks / (kWarps * 2);
+    int64_t s_max = chunks / (kMmaWarps * 2);
     if (s_max < 1) s_max = 1;
     int64_t s = s_want < s_max ? s_want : s_max;
+    (void)p;
     return (int)(s < 1 ? 1 : s);
 }
 
@@ -334,11 +414,11 @@ static int launch_cfg(const IrlsArgs& a, int family, size_t smem, int grid, cuda
     if (family == DLSA_FAMILY_LOGISTIC) {
         auto kern = irls_small_kernel<NT, CH, STAGES, DLSA_FAMILY_LOGISTIC>;
         DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kWarps * 32, smem, st>>>(a);
+        kern<<<grid, kThreads, smem, st>>>(a);
     } else {
         auto kern = irls_small_kernel<NT, CH, STAGES, DLSA_FAMILY_LINEAR>;
         DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kWarps * 32, smem, st>>>(a);
+        kern<<<grid, kThreads, smem, st>>>(a);
     }
     count_launch();
     return check_launch("irls_small_kernel");
@@ -349,12 +429,13 @@ int irls_small_launch(const double* X, int64_t ldx, const double* y, const int64
                       double* loglik, int64_t max_part_rows, void* workspace, size_t workspace_bytes,
                       cudaStream_t st) {
     const int p = px + (icpt ? 1 : 0);
-    SmallCfg c = small_cfg(p);
+    SmallCfg c = small_cfg(px, p);
     const int S = irls_small_slices(K, p, max_part_rows);
     IrlsArgs a;
     a.X = X; a.ldx = ldx; a.y = y; a.part_off = part_off; a.beta = beta; a.active = active;
-    a.K = K; a.px = px; a.p = p; a.icpt = icpt ? 1 : 0; a.S = S; a.Sd = c.Sd;
-    a.aligned = ((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (ldx % 2) == 0 && (px % 2) == 0) ? 1 : 0;
+    a.K = K; a.px = px; a.p = p; a.icpt = icpt ? 1 : 0; a.S = S;
+    // TMA staging copies GR consecutive rows with one bulk copy: rows must be contiguous (ldx == px), 16-byte aligned
+    a.aligned = ((reinterpret_cast<uintptr_t>(X) & 15) == 0 && ldx == px && (px % 2) == 0) ? 1 : 0;
     a.want_ll = loglik != nullptr;
     double *pH = nullptr, *pg = nullptr, *pll = nullptr;
     if (S == 1) {
