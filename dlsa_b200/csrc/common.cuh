@@ -80,12 +80,56 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 
 __device__ __forceinline__ double shfl_xor_f64(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-// logistic link pieces, written exactly as the reference evaluates them:
-//   prob = 1/(1+exp(-eta)) (sklearn predict_proba / R wlse_func.R:52), w = prob*(1-prob) (dlsa/models.py:130)
+// ---- branch-free FP64 link arithmetic ---------------------------------------------------------------------
+// The per-row stage is software-pipelined between DMMAs of the same warp, which only works if it is straight-line
+// code: CUDA's exp() and '/' carry slow-path branches/calls that split the basic block.  These versions are
+// branch-free and accurate to ~1 ulp on the ranges used here.
+
+// exp(x) for x <= 0 (argument clamped at -708: below that 1 + exp(x) == 1 anyway).
+__device__ __forceinline__ double exp_nonpos(double x) {
+    x = fmax(x, -708.0);
+    const double kShift = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
+    const double t = fma(x, 1.4426950408889634074, kShift);
+    const int n = __double2loint(t);
+    const double nf = t - kShift;
+    double r = fma(nf, -6.93147180369123816490e-01, x);  // Cody-Waite: ln2_hi
+    r = fma(nf, -1.90821492927058770002e-10, r);         //             ln2_lo
+    double p = 1.6059043836821613e-10;                   // 1/13!   (|r| <= 0.3466: truncation < 1e-17)
+    p = fma(p, r, 2.08767569878681e-09);                 // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);                // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);                // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);               // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);                 // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);                // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);                // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);                // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);               // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);               // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return p * __hiloint2double((n + 1023) << 20, 0);    // * 2^n, n in [-1022, 0]
+}
+
+// num / den for den in [1, 2]: MUFU.RCP64H seed, two Newton steps, one residual correction.
+__device__ __forceinline__ double div_den_1to2(double num, double den) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    double e = fma(-den, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-den, r, 1.0);
+    r = fma(r, e, r);
+    const double qv = num * r;
+    const double rem = fma(-den, qv, num);
+    return fma(rem, r, qv);
+}
+
+// prob = 1/(1+exp(-eta)) for eta >= 0, exp(eta)/(1+exp(eta)) otherwise — the overflow-free form of
+// sklearn's predict_proba / R wlse_func.R:52; w = prob*(1-prob) is formed by the caller (dlsa/models.py:130).
 __device__ __forceinline__ double sigmoid_f64(double eta) {
-    if (eta >= 0) return 1.0 / (1.0 + exp(-eta));
-    double e = exp(eta);
-    return e / (1.0 + e);
+    const double e = exp_nonpos(-fabs(eta));
+    const double num = (eta >= 0.0) ? 1.0 : e;
+    return div_den_1to2(num, 1.0 + e);
 }
 __device__ __forceinline__ double log1pexp_f64(double eta) { return fmax(eta, 0.0) + log1p(exp(-fabs(eta))); }
 
