@@ -51,12 +51,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int NT, int CH, int STAGES, int FAMILY>
+// REM > 0: p = 8(NT-1) + REM with REM <= 4: the last (ragged) tile row of H is accumulated by DFMA on the fragments
+// already in registers (REM*NT DFMAs per k-step) instead of NT mostly-padding DMMAs; REM == 0: all tiles on DMMA.
+template <int NT, int REM, int CH, int STAGES, int FAMILY>
 __global__ void __launch_bounds__(kThreads, 1) irls_small_kernel(const IrlsArgs a) {
-    constexpr int NTRI = NT * (NT + 1) / 2;
+    constexpr int ND = (REM > 0) ? NT - 1 : NT;  // tile rows on DMMA
+    constexpr int NE = (REM > 0) ? REM : 1;
+    constexpr int NTRI = ND * (ND + 1) / 2;
+    constexpr int EOFF = NTRI * 64;                       // reduction-buffer layout: tiles | edge rows | g | pad
+    constexpr int GOFF = EOFF + ((REM > 0) ? REM * NT * 8 : 0);
     constexpr int GR = CH / 4;   // rows per group (= k-steps per chunk)
     constexpr int NG = CH / 8;   // 8-row groups of the eta stage
-    constexpr int NRED = NTRI * 64 + NT * 8 + 8;
+    constexpr int NRED = GOFF + NT * 8 + 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -256,12 +262,28 @@ __global__ void __launch_bounds__(kThreads, 1) irls_small_kernel(const IrlsArgs 
         const int64_t first = c_lo + m;
         const int my_n = (first < c_hi) ? (int)((c_hi - first + kMmaWarps - 1) / kMmaWarps) : 0;
 
-        double C[NTRI][2];
+        double C[NTRI > 0 ? NTRI : 1][2];
+        double E[NE][NT];
         double gacc[NT];
 #pragma unroll
         for (int t = 0; t < NTRI; t++) C[t][0] = C[t][1] = 0.0;
 #pragma unroll
         for (int t = 0; t < NT; t++) gacc[t] = 0.0;
+#pragma unroll
+        for (int e = 0; e < NE; e++)
+#pragma unroll
+            for (int t = 0; t < NT; t++) E[e][t] = 0.0;
+        // ragged-edge columns 8(NT-1)+e, e < REM: shared-memory column (or the constant intercept / padding)
+        int ecol[NE];
+        bool e_in_x[NE];
+        double e_const[NE];
+#pragma unroll
+        for (int e = 0; e < NE; e++) {
+            const int c = 8 * (NT - 1) + e;
+            e_in_x[e] = c < px;
+            e_const[e] = (c == px && a.icpt) ? 1.0 : 0.0;
+            ecol[e] = e_in_x[e] ? c : 0;
+        }
 
         // fragment element of this lane in k-step ks: row = GR*q + ks (group q), column 8t + a8
         const int frag_base = q * gstride;  // + ks*S + 8t + a8
@@ -293,14 +315,23 @@ __global__ void __launch_bounds__(kThreads, 1) irls_small_kernel(const IrlsArgs 
                 }
 #pragma unroll
                 for (int t = 0; t < NT; t++) {
-                    av[t] = wv * f[t];
+                    if (t < ND) av[t] = wv * f[t];
                     gacc[t] = fma(rv, f[t], gacc[t]);
                 }
 #pragma unroll
-                for (int i = 0; i < NT; i++)
+                for (int i = 0; i < ND; i++)
 #pragma unroll
                     for (int j = 0; j <= i; j++)
                         dmma884(C[i * (i + 1) / 2 + j][0], C[i * (i + 1) / 2 + j][1], av[i], f[j]);
+                if (REM > 0) {
+#pragma unroll
+                    for (int e = 0; e < NE; e++) {
+                        const double xv = Tr[ecol[e]];  // same address for the 8 lanes of a row: broadcast load
+                        const double ae = wv * (e_in_x[e] ? xv : e_const[e]);
+#pragma unroll
+                        for (int t = 0; t < NT; t++) E[e][t] = fma(ae, f[t], E[e][t]);
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&b[2]));  // stage free
@@ -317,9 +348,20 @@ __global__ void __launch_bounds__(kThreads, 1) irls_small_kernel(const IrlsArgs 
             red[t * 64 + a8 * 8 + 2 * q] = C[t][0];
             red[t * 64 + a8 * 8 + 2 * q + 1] = C[t][1];
         }
+        if (REM > 0) {
+#pragma unroll
+            for (int e = 0; e < NE; e++)
+#pragma unroll
+                for (int t = 0; t < NT; t++) {
+                    double v = E[e][t];
+                    v += shfl_xor_f64(v, 1);
+                    v += shfl_xor_f64(v, 2);
+                    if (q == 0) red[EOFF + (e * NT + t) * 8 + a8] = v;
+                }
+        }
         if (q == 0) {
 #pragma unroll
-            for (int t = 0; t < NT; t++) red[NTRI * 64 + 8 * t + a8] = gacc[t];
+            for (int t = 0; t < NT; t++) red[GOFF + 8 * t + a8] = gacc[t];
         }
         named_bar_sync(2, kThreads);  // (B)
     }
@@ -327,28 +369,34 @@ __global__ void __launch_bounds__(kThreads, 1) irls_small_kernel(const IrlsArgs 
     // ---- fixed-order reduction over the 8 MMA warps, then emit (all 12 warps) ------------------------
     double* oH = a.outH + (size_t)blockIdx.x * p * p;
     double* og = a.outg + (size_t)blockIdx.x * p;
-    for (int e = threadIdx.x; e < NTRI * 64 + NT * 8 + 1; e += kThreads) {
+    for (int e = threadIdx.x; e < GOFF + NT * 8 + 1; e += kThreads) {
         double v = 0.0;
-        if (e < NTRI * 64 + NT * 8) {
+        if (e < GOFF + NT * 8) {
 #pragma unroll
             for (int w = 0; w < kMmaWarps; w++) v += ring[(size_t)w * NRED + e];
         }
-        if (e < NTRI * 64) {
+        int r_ = -1, c_ = -1;
+        if (e < EOFF) {  // DMMA tile (i, j): element (mm, nn)
             const int tt = e >> 6, mm = (e >> 3) & 7, nn = e & 7;
             int i = 0;
             while ((i + 1) * (i + 2) / 2 <= tt) i++;
             const int j = tt - i * (i + 1) / 2;
-            const int r_ = 8 * i + mm, c_ = 8 * j + nn;
-            if (r_ < p && c_ < p && (i != j || nn <= mm)) {
+            if (i != j || nn <= mm) { r_ = 8 * i + mm; c_ = 8 * j + nn; }
+        } else if (e < GOFF) {  // ragged edge row 8(NT-1) + ee, column cc (lower triangle incl. diagonal)
+            const int ee = (e - EOFF) / (NT * 8), cc = (e - EOFF) % (NT * 8);
+            if (cc <= 8 * (NT - 1) + ee) { r_ = 8 * (NT - 1) + ee; c_ = cc; }
+        }
+        if (e < GOFF) {
+            if (r_ >= 0 && r_ < p && c_ < p) {
                 const int ro = a.icpt ? (r_ == px ? 0 : r_ + 1) : r_;
                 const int co = a.icpt ? (c_ == px ? 0 : c_ + 1) : c_;
                 oH[(size_t)ro * p + co] = v;
                 oH[(size_t)co * p + ro] = v;
             }
-        } else if (e < NTRI * 64 + NT * 8) {
-            const int c_ = e - NTRI * 64;
-            if (c_ < p) {
-                const int co = a.icpt ? (c_ == px ? 0 : c_ + 1) : c_;
+        } else if (e < GOFF + NT * 8) {
+            const int cg = e - GOFF;
+            if (cg < p) {
+                const int co = a.icpt ? (cg == px ? 0 : cg + 1) : cg;
                 og[co] = v;
             }
         } else if (a.outll != nullptr) {
@@ -409,19 +457,33 @@ int irls_small_slices(int K, int p, int64_t max_part_rows) {
     return (int)(s < 1 ? 1 : s);
 }
 
-template <int NT, int CH, int STAGES>
+template <int NT, int REM, int CH, int STAGES>
 static int launch_cfg(const IrlsArgs& a, int family, size_t smem, int grid, cudaStream_t st) {
     if (family == DLSA_FAMILY_LOGISTIC) {
-        auto kern = irls_small_kernel<NT, CH, STAGES, DLSA_FAMILY_LOGISTIC>;
+        auto kern = irls_small_kernel<NT, REM, CH, STAGES, DLSA_FAMILY_LOGISTIC>;
         DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kThreads, smem, st>>>(a);
     } else {
-        auto kern = irls_small_kernel<NT, CH, STAGES, DLSA_FAMILY_LINEAR>;
+        auto kern = irls_small_kernel<NT, REM, CH, STAGES, DLSA_FAMILY_LINEAR>;
         DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kThreads, smem, st>>>(a);
     }
     count_launch();
     return check_launch("irls_small_kernel");
+}
+
+template <int NT, int CH, int STAGES>
+static int launch_rem(const IrlsArgs& a, int rem, int family, size_t smem, int grid, cudaStream_t st) {
+    if (NT >= 2) {  // ragged last tile row (p % 8 in 1..4) goes to DFMA
+        switch (rem) {
+            case 1: return launch_cfg<NT, (NT >= 2 ? 1 : 0), CH, STAGES>(a, family, smem, grid, st);
+            case 2: return launch_cfg<NT, (NT >= 2 ? 2 : 0), CH, STAGES>(a, family, smem, grid, st);
+            case 3: return launch_cfg<NT, (NT >= 2 ? 3 : 0), CH, STAGES>(a, family, smem, grid, st);
+            case 4: return launch_cfg<NT, ((NT >= 2 && NT <= 6) ? 4 : 0), CH, STAGES>(a, family, smem, grid, st);
+            default: break;
+        }
+    }
+    return launch_cfg<NT, 0, CH, STAGES>(a, family, smem, grid, st);
 }
 
 int irls_small_launch(const double* X, int64_t ldx, const double* y, const int64_t* part_off, int K, int px,
@@ -450,8 +512,9 @@ int irls_small_launch(const double* X, int64_t ldx, const double* y, const int64
         a.outH = pH; a.outg = pg; a.outll = pll;
     }
     const int grid = K * S;
+    const int rem = p % 8;
     int rc = 0;
-#define DLSA_CASE(NT_, CH_, ST_) rc = launch_cfg<NT_, CH_, ST_>(a, family, c.smem, grid, st)
+#define DLSA_CASE(NT_, CH_, ST_) rc = launch_rem<NT_, CH_, ST_>(a, rem, family, c.smem, grid, st)
     if (c.CH == 32 && c.STAGES == 3) {
         switch (c.NT) {
             case 1: DLSA_CASE(1, 32, 3); break;
