@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) irls_small_kernel(const IrlsArgs 
             const double* rs = ws + CH;
             mbar_wait(smem_u32(&b[0]), par);  // X chunk landed (async-proxy writes visible to this warp)
             mbar_wait(smem_u32(&b[1]), par);  // weights / residuals written by the row warp
-#pragma unroll 2
+#pragma unroll
             for (int ks = 0; ks < GR; ks++) {
                 const int row = GR * q + ks;
                 const double wv = ws[row], rv = rs[row];
