@@ -144,11 +144,28 @@ def run_reference(args):
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Library banners (e.g. "NCCL version ...") go to fd 1; keep stdout for the ONE JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -311,7 +328,7 @@ def main():
                "result_check": {"K_eff": comb.K_eff, "path_rows": int(path.beta.shape[0]),
                                 "support_BIC": int((path.beta[path.argmin_BIC] != 0).sum().item()),
                                 "theta_head": [round(v, 6) for v in comb.beta_byOLS[:3].tolist()]}}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
