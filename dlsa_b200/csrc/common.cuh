@@ -111,8 +111,9 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     return p * __hiloint2double((n + 1023) << 20, 0);    // * 2^n, n in [-1022, 0]
 }
 
-// num / den for den in [1, 2]: MUFU.RCP64H seed, two Newton steps, one residual correction.
-__device__ __forceinline__ double div_den_1to2(double num, double den) {
+// num / den for a positive normal den of moderate size: MUFU.RCP64H seed, two Newton steps, one residual
+// correction (correctly rounded or 1 ulp off).
+__device__ __forceinline__ double div_pos(double num, double den) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
     double e = fma(-den, r, 1.0);
@@ -129,8 +130,41 @@ __device__ __forceinline__ double div_den_1to2(double num, double den) {
 __device__ __forceinline__ double sigmoid_f64(double eta) {
     const double e = exp_nonpos(-fabs(eta));
     const double num = (eta >= 0.0) ? 1.0 : e;
-    return div_den_1to2(num, 1.0 + e);
+    return div_pos(num, 1.0 + e);
 }
-__device__ __forceinline__ double log1pexp_f64(double eta) { return fmax(eta, 0.0) + log1p(exp(-fabs(eta))); }
+
+// log(1 + e) for e in [0, 1], branch-free: u = 1 + e is halved when it exceeds sqrt(2), then
+// log(u) = 2 atanh(s), s = (u-1)/(u+1), |s| <= 0.1716 (odd series to s^23: truncation < 2e-19), plus the
+// first-order correction (e - (u-1))/u for the rounding of 1 + e (what makes log1p accurate for tiny e).
+__device__ __forceinline__ double log1p_01(double e) {
+    const double u = 1.0 + e;
+    const double c = e - (u - 1.0);             // rounding error of u (exact)
+    const bool big = u > 1.4142135623730951;
+    const double v = big ? 0.5 * u : u;         // [0.7071, 1.4142]
+    // v - 1 without cancellation error: for !big it is e - c; for big it is 0.5*u - 1 (exact: u in (1.41, 2])
+    const double vm1 = big ? fma(0.5, u, -1.0) : (u - 1.0);
+    const double s = div_pos(vm1, v + 1.0);
+    const double z = s * s;
+    double p = 1.0 / 23.0;
+    p = fma(p, z, 1.0 / 21.0);
+    p = fma(p, z, 1.0 / 19.0);
+    p = fma(p, z, 1.0 / 17.0);
+    p = fma(p, z, 1.0 / 15.0);
+    p = fma(p, z, 1.0 / 13.0);
+    p = fma(p, z, 1.0 / 11.0);
+    p = fma(p, z, 1.0 / 9.0);
+    p = fma(p, z, 1.0 / 7.0);
+    p = fma(p, z, 1.0 / 5.0);
+    p = fma(p, z, 1.0 / 3.0);
+    p = p * z;                                  // atanh(s)/s - 1
+    double r = fma(2.0 * s, p, 2.0 * s);        // log(v)
+    r += big ? 6.93147180559945286227e-01 : 0.0;
+    double ru;                                  // d log(u)/du * c = c / u: c <= 2^-53, a 20-bit reciprocal is plenty
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ru) : "d"(u));
+    return fma(c, ru, r);
+}
+__device__ __forceinline__ double log1pexp_f64(double eta) {
+    return fmax(eta, 0.0) + log1p_01(exp_nonpos(-fabs(eta)));
+}
 
 }  // namespace dlsa
