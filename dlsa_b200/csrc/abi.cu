@@ -30,9 +30,9 @@ int check_launch(const char* what) {
 int irls_small_launch(const double*, int64_t, const double*, const int64_t*, int, int, int, int, const double*,
                       const int*, double*, double*, double*, int64_t, void*, size_t, cudaStream_t);
 size_t irls_small_workspace_bytes(int K, int p, int64_t max_part_rows);
-int irls_large_launch(const double*, int64_t, const double*, const int64_t*, int, int, int, int, const double*,
+int irls_tiled_launch(const double*, int64_t, const double*, const int64_t*, int, int, int, int, const double*,
                       const int*, double*, double*, double*, int64_t, void*, size_t, cudaStream_t);
-size_t irls_large_workspace_bytes(int K, int p, int64_t max_part_rows);
+size_t irls_tiled_workspace_bytes(int K, int p, int64_t max_part_rows);
 size_t chol_workspace_bytes(int K, int p);
 int chol_launch(const double*, const double*, int, int, int, double*, double*, double*, int*, int*, int*, int*, double,
                 double, double, void*, size_t, cudaStream_t);
@@ -64,7 +64,7 @@ unsigned long long dlsa_launch_count(void) { return g_launches.load(std::memory_
 size_t dlsa_irls_pass_workspace_bytes(int K, int p, int64_t max_part_rows) {
     if (K <= 0 || p <= 0) return 0;
     return p <= kSmallMaxP ? irls_small_workspace_bytes(K, p, max_part_rows)
-                           : irls_large_workspace_bytes(K, p, max_part_rows);
+                           : irls_tiled_workspace_bytes(K, p, max_part_rows);
 }
 
 int dlsa_irls_pass_f64(const double* X, int64_t ldx, const double* y, const int64_t* part_off, int K, int px,
@@ -83,7 +83,7 @@ int dlsa_irls_pass_f64(const double* X, int64_t ldx, const double* y, const int6
     if (p <= kSmallMaxP)
         return irls_small_launch(X, ldx, y, part_off, K, px, fit_intercept, family, beta, active, g, H, loglik,
                                  max_part_rows, workspace, workspace_bytes, st);
-    return irls_large_launch(X, ldx, y, part_off, K, px, fit_intercept, family, beta, active, g, H, loglik,
+    return irls_tiled_launch(X, ldx, y, part_off, K, px, fit_intercept, family, beta, active, g, H, loglik,
                              max_part_rows, workspace, workspace_bytes, st);
 }
 

@@ -274,6 +274,34 @@ def test_irls_pass_large_p_matches_oracle(eng, px, icpt, sizes):
         assert np.array_equal(H[k], H[k].T)
 
 
+@pytest.mark.parametrize("px,icpt", [(181, True), (181, False), (99, False), (301, True)])
+def test_large_p_odd_px_padded_pitch_takes_tma_path(eng, px, icpt):
+    """odd px stored with an even row pitch (what the airline one-hot expand produces): rows are 16-byte aligned, the
+    TMA row copy drags the padding column along and the kernel must repair it (the padding holds NaN here)."""
+    rng = np.random.default_rng(px)
+    sizes = [1700, 0, 811]
+    off = ragged_offsets(sizes)
+    n = int(off[-1])
+    p = px + int(icpt)
+    big = np.full((n, px + 1), np.nan)
+    big[:, :px] = rng.random((n, px)) - 0.5
+    y = (rng.random(n) < 0.4).astype(np.float64)
+    beta = rng.standard_normal((len(sizes), p)) * (2.0 / np.sqrt(p))
+    Xd = dev(big)[:, :px]
+    assert Xd.stride(0) == px + 1
+    g, H, ll = eng.irls_pass(Xd, dev(y), dev(off, torch.int64), dev(beta), fit_intercept=icpt)
+    g, H, ll = g.cpu().numpy(), H.cpu().numpy(), ll.cpu().numpy()
+    for k, nk in enumerate(sizes):
+        Xk = big[off[k]:off[k + 1], :px]
+        if icpt:
+            Xk = np.concatenate([np.ones((nk, 1)), Xk], axis=1)
+        g0, H0, ll0 = onp.irls_pass(Xk, y[off[k]:off[k + 1]], beta[k])
+        assert np.allclose(g[k], g0, rtol=1e-10, atol=1e-10), (k, nk)
+        assert relfro(H[k], H0) < 1e-13 if nk else np.all(H[k] == 0)
+        assert abs(ll[k] - ll0) <= 1e-11 * max(1.0, abs(ll0))
+        assert np.array_equal(H[k], H[k].T)
+
+
 def test_large_p_sliced_partitions(eng):
     """few big partitions at p=100: slices + fixed-order slice reduce."""
     rng = np.random.default_rng(9)

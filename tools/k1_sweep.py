@@ -66,7 +66,8 @@ def main():
     for name in args.cases.split(","):
         n, px, K, icpt, fam, law = CASES[name]
         p = px + int(icpt)
-        X = torch.empty(n, px, dtype=torch.float64, device=dev)
+        ldx = px + (px & 1)  # odd px is stored with an even row pitch (16-byte aligned rows -> TMA row copies)
+        X = torch.zeros(n, ldx, dtype=torch.float64, device=dev)[:, :px]
         y = torch.empty(n, dtype=torch.float64, device=dev)
         chunk = 5_000_000
         beta_true = synth.true_beta(px) * (0.3 if px > 60 else 1.0)
