@@ -8,14 +8,16 @@
 //     to (sibling CTA, sub-partition, warp, slot) so that every sub-partition's FP64 pipe carries the same number of
 //     DMMAs (the pipe is per sub-partition; an unbalanced deal idles it).  Every tile has exactly one owner: no
 //     cross-warp reduction, bitwise reproducible.
-//   * CTA = 16 warps (one idle, see kTWarps), one CTA per SM.  12 MMA warps (setmaxnreg 144) own up to NBW blocks each and do nothing but
-//     LDS + DMUL + DMMA.  2 row warps compute eta = x'beta (lane = column stripe, 4 rows in flight, transposed
-//     butterfly reduction), the sigmoid, w and r one chunk ahead, and accumulate g = X'r.  1 producer warp keeps a
-//     ring of 16-row chunks full with one TMA bulk copy per row (UBLKCP; rows land with a stride == 4 mod 16
-//     doubles so that fragment loads are bank-conflict free), gated by full / wr / empty mbarriers per stage.
+//   * CTA = 16 warps, one CTA per SM.  12 MMA warps (setmaxnreg 144) own up to NBW blocks each and do nothing but
+//     LDS + DMUL + DMMA, in a straight-line body specialised on (blocks owned, any partial block).  3 row warps
+//     take the 8-row half-chunks round-robin: eta = x'beta (lane = column stripe, 4 rows in flight, transposed
+//     butterfly reduction), the sigmoid, w and r ahead of the MMA warps, and g = X'r.  1 producer warp keeps a ring
+//     of 16-row chunks full with one TMA bulk copy per row (UBLKCP; rows land with a pitch == 4 mod 16 doubles so
+//     that fragment loads are bank-conflict free), gated by full / wr / empty mbarriers per stage.
 //   * Sibling CTAs (tile group tg = blockIdx.x % TG) are adjacent in the grid, run at the same time and read the
 //     same rows: X comes from HBM once and from L2 TG-1 times.
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -23,9 +25,8 @@
 namespace dlsa {
 
 constexpr int kTMma = 12;                       // MMA warps
-constexpr int kTRow = 2;                        // row warps
-constexpr int kTWarps = 16;                     // 12 MMA + 2 row + producer + 1 idle: setmaxnreg acts on whole
-                                                // warpgroups (4 aligned warps), so the tail group must be complete
+constexpr int kTRow = 3;                        // row warps
+constexpr int kTWarps = kTMma + kTRow + 1;      // + producer = 16; setmaxnreg acts on whole warpgroups (4 aligned warps)
 constexpr int kTThreads = kTWarps * 32;         // 512 -> 128 registers per thread at launch
 constexpr int kTCH = 16;                        // rows per chunk
 constexpr int kTMaxTG = 16;
@@ -78,15 +79,14 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
     const int64_t c_hi = (c_lo + cps < nchunks) ? (c_lo + cps) : nchunks;
     const int my_n = (c_hi > c_lo) ? (int)(c_hi - c_lo) : 0;
 
-    // ---- shared memory: tiles [ST][CH*Sd] | ws [ST][CH] | rs [ST][CH] | beta_s [Sd] | gred [JMAX*32] | llred | bars
+    // ---- shared memory: tiles [ST][CH*Sd] | ws [ST][CH] | rs [ST][CH] | beta_s [Sd] | gred [2][JMAX*32+2] | bars
     const int stage_doubles = kTCH * Sd;
     double* tiles = reinterpret_cast<double*>(smem_raw);
     double* ws_all = tiles + (size_t)ST * stage_doubles;
     double* rs_all = ws_all + ST * kTCH;
     double* beta_s = rs_all + ST * kTCH;
     double* gred = beta_s + Sd;
-    double* llred = gred + JMAX * 32 + 8;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(llred + 8);  // [ST][3]: full, wr, empty
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gred + 2 * (JMAX * 32 + 2));  // [ST][3]: full, wr, empty
 
     for (int c = tid; c < Sd; c += kTThreads) {
         double bv = 0.0;
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
     if (tid < ST) {
         uint64_t* b = bars + tid * 3;
         mbar_init(smem_u32(&b[0]), a.aligned ? 1u : 32u);
-        mbar_init(smem_u32(&b[1]), (uint32_t)kTRow);
-        mbar_init(smem_u32(&b[2]), (uint32_t)(kTMma + kTRow));
+        mbar_init(smem_u32(&b[1]), 2u);                       // the two half-chunks
+        mbar_init(smem_u32(&b[2]), (uint32_t)(kTMma + 2));
         fence_mbar_init();
     }
     fence_proxy_async();
@@ -116,15 +116,14 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
     const double* yp = a.y + row_lo;
 
     if (warp == kTWarps - 1) {
-        t_setmaxnreg_dec<kTRegsAux>();  // idle warp: completes the aux warpgroup, nothing else
-    } else if (warp == kTWarps - 2) {
         // =========================== producer warp: one bulk copy per row ==================================
         t_setmaxnreg_dec<kTRegsAux>();
         const uint32_t row_bytes = (uint32_t)a.copy_cols * 8u;
+        int st = 0;
+        uint32_t par = 1;  // parity of the empty phase a refill waits for; flips to 0 at the first wrap
         for (int ci = 0; ci < my_n; ci++) {
-            const int st = ci % ST;
             if (ci >= ST) {
-                mbar_wait(smem_u32(&bars[st * 3 + 2]), (uint32_t)((ci / ST - 1) & 1));
+                mbar_wait(smem_u32(&bars[st * 3 + 2]), par);
                 fence_proxy_async();
             }
             const int64_t r0 = (c_lo + ci) * kTCH;
@@ -138,18 +137,21 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
                     bulk_g2s(smem_u32(dst + (size_t)lane * Sd), Xp + (r0 + lane) * a.ldx, row_bytes, bar);
             } else {
                 for (int e = lane; e < valid * px; e += 32) {
-                    const int row = e / px, col = e - row * px;
-                    cp_async8(smem_u32(dst + (size_t)row * Sd + col), Xp + (r0 + row) * a.ldx + col);
+                    const int rw_ = e / px, col = e - rw_ * px;
+                    cp_async8(smem_u32(dst + (size_t)rw_ * Sd + col), Xp + (r0 + rw_) * a.ldx + col);
                 }
                 cp_async_mbar_arrive_noinc(bar);
             }
+            if (++st == ST) { st = 0; par ^= 1u; }
         }
-    } else if (warp >= kTMma) {  // warps kTMma .. kTMma+kTRow-1
+    } else if (warp >= kTMma) {
         // =========================== row warps: eta, sigmoid, w, r (+ g, log-likelihood on sibling 0) ========
+        // The 3 row warps take the half-chunks (8 rows) of the stream round-robin; a half-chunk is two 4-row batches
+        // whose sigmoid chains interleave.
         t_setmaxnreg_dec<kTRegsAux>();
         const int rw = warp - kTMma;
         const int bit4 = (lane >> 4) & 1, bit3 = (lane >> 3) & 1;
-        const int rr = 2 * bit4 + bit3;        // row of the 4-row batch this lane finishes
+        const int rr = 2 * bit4 + bit3;        // row of a 4-row batch this lane finishes
         const bool lead = (lane & 7) == 0;
         const bool fix_pad = a.copy_cols > px;  // odd px: the copy drags one foreign column along
         const double pad_val = a.icpt ? 1.0 : 0.0;
@@ -158,23 +160,32 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
 #pragma unroll
         for (int j = 0; j < JMAX; j++) gacc[j] = 0.0;
         double g_icpt = 0.0, llacc = 0.0;
+        const int n_half = 2 * my_n;
+        auto load_y = [&](int h, int bt) -> double {
+            const int64_t r = (c_lo + (h >> 1)) * kTCH + (h & 1) * 8 + bt * 4 + rr;
+            return (h < n_half && r < n_k) ? __ldg(yp + r) : 0.0;
+        };
+        double y_next[2] = {load_y(rw, 0), load_y(rw, 1)};
+        int st = 0, cur = 0;
+        uint32_t par = 0;
 
-        for (int ci = 0; ci < my_n; ci++) {
-            const int st = ci % ST;
-            const uint32_t par = (uint32_t)((ci / ST) & 1);
+        for (int h = rw; h < n_half; h += kTRow) {
+            const int ci = h >> 1, hb = (h & 1) * 8;
+            while (cur < ci) { cur++; if (++st == ST) { st = 0; par ^= 1u; } }
             const int64_t r0 = (c_lo + ci) * kTCH;
             const int valid = (n_k - r0 < kTCH) ? (int)(n_k - r0) : kTCH;
+            const double y_cur[2] = {y_next[0], y_next[1]};
+            y_next[0] = load_y(h + kTRow, 0);
+            y_next[1] = load_y(h + kTRow, 1);
             double* T = tiles + (size_t)st * stage_doubles;
-            double* ws = ws_all + st * kTCH;
-            double* rs = rs_all + st * kTCH;
             mbar_wait(smem_u32(&bars[st * 3 + 0]), par);
             double rv_b[2];
 #pragma unroll
             for (int bt = 0; bt < 2; bt++) {
-                const int rb = rw * 8 + bt * 4;
+                const int rb = hb + bt * 4;
                 const int row = rb + rr;
                 const bool rowvalid = row < valid;
-                const double yv = rowvalid ? __ldg(yp + r0 + row) : 0.0;
+                const double yv = y_cur[bt];
                 double wv, rv;
                 if (FAMILY == DLSA_FAMILY_LOGISTIC) {
                     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -212,18 +223,18 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
                 rv = rowvalid ? rv : 0.0;
                 rv_b[bt] = rv;
                 if (lead) {
-                    ws[row] = wv;
-                    rs[row] = rv;
+                    ws_all[st * kTCH + row] = wv;
+                    rs_all[st * kTCH + row] = rv;
                     if (fix_pad) T[(size_t)row * Sd + px] = pad_val;
                 }
             }
             if (fix_pad) fence_proxy_async();  // generic-proxy writes into a stage the TMA will overwrite later
             __syncwarp();
-            if (lane == 0) t_mbar_arrive(smem_u32(&bars[st * 3 + 1]));  // w/r of this warp's 8 rows are ready
+            if (lane == 0) t_mbar_arrive(smem_u32(&bars[st * 3 + 1]));  // w/r of these 8 rows are ready
             if (tg == 0) {
 #pragma unroll
                 for (int bt = 0; bt < 2; bt++) {
-                    const double* Tb = T + (size_t)(rw * 8 + bt * 4) * Sd + lane;
+                    const double* Tb = T + (size_t)(hb + bt * 4) * Sd + lane;
                     const double r0v = __shfl_sync(0xffffffffu, rv_b[bt], 0);
                     const double r1v = __shfl_sync(0xffffffffu, rv_b[bt], 8);
                     const double r2v = __shfl_sync(0xffffffffu, rv_b[bt], 16);
@@ -247,27 +258,30 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
             if (lane == 0) t_mbar_arrive(smem_u32(&bars[st * 3 + 2]));  // done reading the stage
         }
         if (tg == 0) {
-            // intercept gradient and log-likelihood live on the 4 group leaders: sum them
+            // intercept gradient and log-likelihood live on the 4 group leaders: sum them, then the 3 row warps
             g_icpt += shfl_xor_f64(g_icpt, 8);
             g_icpt += shfl_xor_f64(g_icpt, 16);
             llacc += shfl_xor_f64(llacc, 8);
             llacc += shfl_xor_f64(llacc, 16);
-            if (rw == 1) {
+            if (rw > 0) {
+                double* gr = gred + (size_t)(rw - 1) * (JMAX * 32 + 2);
 #pragma unroll
-                for (int j = 0; j < JMAX; j++) gred[lane + 32 * j] = gacc[j];
-                if (lane == 0) { llred[0] = g_icpt; llred[1] = llacc; }
+                for (int j = 0; j < JMAX; j++) gr[lane + 32 * j] = gacc[j];
+                if (lane == 0) { gr[JMAX * 32] = g_icpt; gr[JMAX * 32 + 1] = llacc; }
             }
-            asm volatile("bar.sync 1, 64;" ::: "memory");
+            asm volatile("bar.sync 1, 96;" ::: "memory");
             if (rw == 0) {
                 double* og = a.outg + (size_t)item * p;
+                const double* g1 = gred;
+                const double* g2 = gred + (JMAX * 32 + 2);
 #pragma unroll
                 for (int j = 0; j < JMAX; j++) {
                     const int c = lane + 32 * j;
-                    if (c < px) og[c + a.icpt] = gacc[j] + gred[c];
+                    if (c < px) og[c + a.icpt] = (gacc[j] + g1[c]) + g2[c];
                 }
                 if (lane == 0) {
-                    if (a.icpt) og[0] = g_icpt + llred[0];
-                    if (a.outll != nullptr) a.outll[item] = llacc + llred[1];
+                    if (a.icpt) og[0] = (g_icpt + g1[JMAX * 32]) + g2[JMAX * 32];
+                    if (a.outll != nullptr) a.outll[item] = (llacc + g1[JMAX * 32 + 1]) + g2[JMAX * 32 + 1];
                 }
             }
         }
@@ -276,12 +290,16 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
         t_setmaxnreg_inc<kTRegsMma>();
         uint32_t bmask[NBW];
         int offA[NBW], offB[NBW];
+        int nb = 0;
+        bool pred = false;
 #pragma unroll
         for (int b = 0; b < NBW; b++) {
             const uint32_t e = a.sched[(tg * kTMma + warp) * kTMaxNBW + b];
             bmask[b] = e & 0xffu;
             offA[b] = 16 * (int)((e >> 8) & 0xffu) + a8;    // column of tile row 2m (tile row 2m+1 is +8)
             offB[b] = 32 * (int)((e >> 16) & 0xffu) + a8;   // column of tile column 4J (+8 per tile)
+            if (bmask[b]) nb = b + 1;                       // slots fill in order
+            if (bmask[b] != 0u && bmask[b] != 0xffu) pred = true;
         }
         double C[NBW][2][4][2];
 #pragma unroll
@@ -291,44 +309,49 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) C[b][ii][jj][0] = C[b][ii][jj][1] = 0.0;
 
-        for (int ci = 0; ci < my_n; ci++) {
-            const int st = ci % ST;
-            const uint32_t par = (uint32_t)((ci / ST) & 1);
-            mbar_wait(smem_u32(&bars[st * 3 + 0]), par);  // rows landed (async-proxy writes visible to this warp)
-            mbar_wait(smem_u32(&bars[st * 3 + 1]), par);  // w written, pad column repaired
-            const double* T = tiles + (size_t)st * stage_doubles + (size_t)q * Sd;
-            const double* ws = ws_all + st * kTCH + q;
+        // one straight-line body per (number of blocks, any partial block): loads are unconditional (every column a
+        // block can name exists in shared memory), so ptxas can hoist them across the DMMAs
+        auto run = [&](auto nb_c, auto pred_c) {
+            constexpr int NB = decltype(nb_c)::value;
+            constexpr bool PRED = decltype(pred_c)::value;
+            int st = 0;
+            uint32_t par = 0;
+            for (int ci = 0; ci < my_n; ci++) {
+                mbar_wait(smem_u32(&bars[st * 3 + 0]), par);  // rows landed (async-proxy writes visible here)
+                mbar_wait(smem_u32(&bars[st * 3 + 1]), par);  // w written, pad column repaired
+                const double* T = tiles + (size_t)st * stage_doubles + (size_t)q * Sd;
+                const double* ws = ws_all + st * kTCH + q;
 #pragma unroll
-            for (int ks = 0; ks < kTCH / 4; ks++) {
-                const double wv = ws[4 * ks];
-                const double* Tr = T + (size_t)(4 * ks) * Sd;  // row 4ks + q
+                for (int ks = 0; ks < kTCH / 4; ks++) {
+                    const double wv = ws[4 * ks];
+                    const double* Tr = T + (size_t)(4 * ks) * Sd;  // row 4ks + q
 #pragma unroll
-                for (int b = 0; b < NBW; b++) {
-                    if (bmask[b] == 0xffu) {
+                    for (int b = 0; b < NB; b++) {
                         const double a0 = Tr[offA[b]] * wv, a1 = Tr[offA[b] + 8] * wv;
                         double f[4];
 #pragma unroll
                         for (int jj = 0; jj < 4; jj++) f[jj] = Tr[offB[b] + 8 * jj];
 #pragma unroll
                         for (int jj = 0; jj < 4; jj++) {
-                            dmma884(C[b][0][jj][0], C[b][0][jj][1], a0, f[jj]);
-                            dmma884(C[b][1][jj][0], C[b][1][jj][1], a1, f[jj]);
-                        }
-                    } else if (bmask[b] != 0u) {
-                        const double a0 = Tr[offA[b]] * wv, a1 = Tr[offA[b] + 8] * wv;
-#pragma unroll
-                        for (int jj = 0; jj < 4; jj++) {
-                            if (bmask[b] & (0x11u << jj)) {
-                                const double fv = Tr[offB[b] + 8 * jj];
-                                if (bmask[b] & (1u << jj)) dmma884(C[b][0][jj][0], C[b][0][jj][1], a0, fv);
-                                if (bmask[b] & (16u << jj)) dmma884(C[b][1][jj][0], C[b][1][jj][1], a1, fv);
-                            }
+                            if (!PRED || (bmask[b] & (1u << jj))) dmma884(C[b][0][jj][0], C[b][0][jj][1], a0, f[jj]);
+                            if (!PRED || (bmask[b] & (16u << jj))) dmma884(C[b][1][jj][0], C[b][1][jj][1], a1, f[jj]);
                         }
                     }
                 }
+                __syncwarp();
+                if (lane == 0) t_mbar_arrive(smem_u32(&bars[st * 3 + 2]));  // done with the stage
+                if (++st == ST) { st = 0; par ^= 1u; }
             }
-            __syncwarp();
-            if (lane == 0) t_mbar_arrive(smem_u32(&bars[st * 3 + 2]));  // done with the stage
+        };
+        using std::integral_constant;
+        if (nb == 0) run(integral_constant<int, 0>{}, integral_constant<bool, false>{});
+        else if (nb == 1 && !pred) run(integral_constant<int, 1>{}, integral_constant<bool, false>{});
+        else if (nb == 1) run(integral_constant<int, 1>{}, integral_constant<bool, true>{});
+        else if (nb == 2 && !pred) run(integral_constant<int, 2>{}, integral_constant<bool, false>{});
+        else if (nb == 2) run(integral_constant<int, 2>{}, integral_constant<bool, true>{});
+        else if constexpr (NBW >= 3) {
+            if (!pred) run(integral_constant<int, NBW>{}, integral_constant<bool, false>{});
+            else run(integral_constant<int, NBW>{}, integral_constant<bool, true>{});
         }
 
         // ---- emit: every tile has exactly one owner --------------------------------------------------------
@@ -431,7 +454,7 @@ static TiledCfg tiled_cfg(int px, int p) {
     if (cols < px + 1) cols = px + 1;
     c.Sd = cols;
     while (c.Sd % 16 != 4) c.Sd++;
-    const size_t fixed = ((size_t)c.Sd + (size_t)c.JMAX * 32 + 8 + 8) * 8 + 256;
+    const size_t fixed = ((size_t)c.Sd + 2 * ((size_t)c.JMAX * 32 + 2)) * 8 + 256;
     const size_t per_stage = ((size_t)kTCH * c.Sd + 2 * kTCH) * 8 + 3 * 8;
     int st = (int)((220 * 1024 - fixed) / per_stage);
     c.stages = st > 8 ? 8 : st;
