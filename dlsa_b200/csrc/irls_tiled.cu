@@ -10,7 +10,7 @@
 //     bitwise reproducible.  A diagonal block is PARTIAL (only tiles on or below the diagonal exist): a warp gets
 //     at most one, in its last slot, and runs a body compiled for that block's shape — a predicated-off DMMA
 //     still occupies the FP64 pipe for its 16 cycles (measured), so masking by predicate is not an option.
-//   * All heavy FP64 work lives in the 12 MMA warps (setmaxnreg 144), interleaved with their DMMAs where it costs
+//   * All heavy FP64 work lives in the 12 MMA warps (setmaxnreg 152), interleaved with their DMMAs where it costs
 //     only its pipe cycles: the Gram blocks; g = X'r (4 DFMAs per k-step in the warp that owns a column group's
 //     diagonal block, reusing its B fragments; the intercept column is an ordinary column of ones in shared
 //     memory); and the partial dot products of eta = x'beta for a chunk a few ahead (lane = column stripe, 4 rows
@@ -37,8 +37,8 @@ constexpr int kTThreads = kTWarps * 32;         // 512 -> 128 registers per thre
 constexpr int kTCH = 16;                        // rows per chunk
 constexpr int kTMaxTG = 16;
 constexpr int kTNBW = 3;                        // block slots per MMA warp
-constexpr int kTRegsMma = 144;
-constexpr int kTRegsAux = 80;
+constexpr int kTRegsMma = 152;
+constexpr int kTRegsAux = 56;
 static_assert(kTMma * kTRegsMma + (kTWarps - kTMma) * kTRegsAux == kTWarps * 128, "register pool");
 static_assert(kTMma % 4 == 0 && kTWarps % 4 == 0, "setmaxnreg needs whole warpgroups");
 constexpr int kTiledMaxP = 512;
@@ -518,8 +518,12 @@ static TiledCfg tiled_cfg(int px, int p) {
     const size_t fixed = ((size_t)c.Sd + 4) * 8 + 256;
     const size_t per_stage = ((size_t)kTCH * c.Sd + 3 * kTCH) * 8 + 4 * 8;
     int st = (int)((220 * 1024 - fixed) / per_stage);
-    c.stages = st > 8 ? 8 : st;
-    c.lookahead = c.stages >= 4 ? 3 : 2;
+    c.stages = st > 12 ? 12 : st;
+    // chunks between the eta partial sums of a chunk and the DMMAs that need its w: the link warp needs ~2 chunk times,
+    // and the rows of chunk ci+LA must have landed, i.e. ST-LA chunk times must cover the HBM latency
+    c.lookahead = (c.stages - 1) / 2;
+    if (c.lookahead > 5) c.lookahead = 5;
+    if (c.lookahead < 2) c.lookahead = 2;
     c.smem = fixed + per_stage * c.stages;
     return c;
 }
