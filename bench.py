@@ -2,7 +2,7 @@
 """bench.py — DLSA rows/sec on B200 (BASELINE.json metric), one JSON line on stdout.
 
 A "step" is one whole pass of the hot path over the synthetic workload: every Newton pass (fused K1 kernel +
-batched Cholesky update), the final Sig_inv pass, the one-round combine (+ one NCCL allreduce when N>1) and the
+batched Cholesky update; the last pass's H is Sig_inv at the returned coefficients), the one-round combine (+ one NCCL allreduce when N>1) and the
 LARS path with AIC/BIC selection.  Workload at N=1 = BASELINE.json configs[1]: simulated logistic regression
 n=1e8, p=50, 1024 partitions (40.8 GB of float64 in HBM).  N>1 is weak scaling: every rank holds its own
 1e8-row / 1024-partition shard of the same counter-based synthetic stream (global row index keyed).
@@ -269,14 +269,12 @@ def main():
             yh = torch.empty(n, dtype=torch.float64, pin_memory=True)
             Xh.copy_(X)
             yh.copy_(y)
-            offh = off.cpu().pin_memory()
+            offh = off.cpu()
             torch.cuda.synchronize()
 
             def e2e_step():
-                X.copy_(Xh, non_blocking=True)
-                y.copy_(yh, non_blocking=True)
-                offd = offh.to(dev, non_blocking=True)
-                f_, c_, p_ = engine.dlsa_fit(X, y, offd, fit_intercept=False, sample_size=n_total, type="lar")
+                f_, c_, p_ = engine.dlsa_fit_host(Xh, yh, offh, fit_intercept=False, sample_size=n_total, type="lar",
+                                                  device=dev, buffers=(X, y))
                 res = torch.cat([c_.beta_byOLS, c_.beta_byONESHOT, c_.Sig_inv_sum.view(-1), p_.beta[p_.argmin_BIC],
                                  p_.beta[p_.argmin_AIC], p_.BIC, p_.AIC]).cpu()
                 return res
@@ -296,7 +294,8 @@ def main():
             e2e = {"value": n_total / (ems * 1e-3), "unit": UNIT,
                    "h2d_bytes_per_step": int(Xh.numel() * 8 + yh.numel() * 8 + offh.numel() * 8),
                    "d2h_bytes_per_step": int(res.numel() * 8), "ms_per_step": ems, "steps": nsteps,
-                   "api": "dlsa_b200.engine.dlsa_fit on pinned host X/y copied to HBM each step"}
+                   "api": "dlsa_b200.engine.dlsa_fit_host: pinned host X/y/offsets in, 16 partition blocks whose H2D copies "
+                          "overlap the fits of earlier blocks, combined estimates + LARS path read back to the host"}
             del Xh, yh
         except Exception as ex:  # e.g. not enough host memory to pin the shard
             e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}

@@ -118,7 +118,11 @@ __global__ void __launch_bounds__(kCholThreads) chol_kernel(const double* __rest
         return;
     }
     const double scale = (md > damp_above) ? damp_factor : 1.0;  // dlsa/R/wlse_func.R:56-60
-    for (int i = threadIdx.x; i < p; i += blockDim.x) beta[(size_t)k * p + i] += scale * xs[i];
+    // A step with max|delta| <= tol is below the solver's resolution: it is NOT applied, so that the H of this
+    // pass is Sig_inv evaluated exactly at the returned coefficients (dlsa/models.py:114,130) and the caller
+    // needs no extra pass for it.
+    if (md > tol)
+        for (int i = threadIdx.x; i < p; i += blockDim.x) beta[(size_t)k * p + i] += scale * xs[i];
     if (threadIdx.x == 0) {
         if (max_delta) max_delta[k] = md;
         iters[k] += 1;

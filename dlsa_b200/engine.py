@@ -30,7 +30,7 @@ class EngineConfig:
     max_iter: int = 50
     damp_above: float = 5.0
     damp_factor: float = 0.01
-    want_loglik: bool = True
+    want_loglik: bool = False   # True: one extra fused pass that also returns every partition's log-likelihood
 
 
 @dataclasses.dataclass
@@ -106,7 +106,7 @@ def _check_inputs(X, y, part_offsets):
 
 
 def irls_pass(X, y, part_offsets, beta, fit_intercept=False, family=_lib.FAMILY_LOGISTIC, active=None,
-              max_part_rows=None, want_loglik=True, out=None, workspace=None):
+              max_part_rows=None, want_loglik=True, out=None, workspace=None, full=None):
     """One fused pass (K1) over all partitions: returns (g[K,p], H[K,p,p], loglik[K] or None)."""
     dev, y = _check_inputs(X, y, part_offsets)
     K = part_offsets.numel() - 1
@@ -132,7 +132,7 @@ def irls_pass(X, y, part_offsets, beta, fit_intercept=False, family=_lib.FAMILY_
           "dlsa_irls_pass_f64")
     if PASS_EVENTS is not None:
         e1.record()
-        PASS_EVENTS.append((e0, e1, active is None))
+        PASS_EVENTS.append((e0, e1, (active is None) if full is None else bool(full)))
     return g, H, ll
 
 
@@ -143,8 +143,8 @@ def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torc
 
     X [n, px] float64 row-major on the GPU with each partition's rows contiguous; ``part_offsets`` int64 [K+1].
     Newton iterations = K1 (fused pass) + K2 (batched Cholesky update) until every partition has
-    max|delta| <= tol; one more K1 at the returned coefficients gives Sig_inv (dlsa/models.py:114,130),
-    then K3 gives Sig_invMcoef (:131).  With an intercept it is coefficient 0 (:116-122).
+    max|delta| <= tol.  K2 does not apply a step that small, so the H of a partition's last pass is Sig_inv at exactly
+    the coefficients it returns (dlsa/models.py:114,130); K3 then gives Sig_invMcoef (:131).  With an intercept it is coefficient 0 (:116-122).
     """
     cfg = config or EngineConfig()
     dev, y = _check_inputs(X, y, part_offsets)
@@ -156,7 +156,7 @@ def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torc
     beta = torch.zeros(K, p, dtype=_F64, device=dev) if beta_init is None else beta_init.to(dev, _F64).clone()
     g = torch.zeros(K, p, dtype=_F64, device=dev)
     H = torch.zeros(K, p, p, dtype=_F64, device=dev)
-    ll = torch.zeros(K, dtype=_F64, device=dev)
+    ll = torch.zeros(K, dtype=_F64, device=dev) if cfg.want_loglik else None
     status = torch.full((K,), _lib.ST_NOT_CONVERGED, dtype=torch.int32, device=dev)
     active = torch.ones(K, dtype=torch.int32, device=dev)
     iters = torch.zeros(K, dtype=torch.int32, device=dev)
@@ -165,26 +165,35 @@ def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torc
     ws_pass = _workspace(lib.dlsa_irls_pass_workspace_bytes(K, p, max_rows), dev)
     ws_chol = _workspace(lib.dlsa_newton_update_workspace_bytes(K, p), dev)
     passes = 0
+    left = K
     for _ in range(cfg.max_iter):
         irls_pass(X, y, part_offsets, beta, fit_intercept, _lib.FAMILY_LOGISTIC, active, max_rows,
-                  want_loglik=False, out=(g, H, None), workspace=ws_pass)
+                  want_loglik=False, out=(g, H, None), workspace=ws_pass, full=(left == K))
         passes += 1
         n_active.zero_()
         check(lib.dlsa_newton_update_f64(H.data_ptr(), g.data_ptr(), K, p, beta.data_ptr(), max_delta.data_ptr(),
                                          status.data_ptr(), active.data_ptr(), iters.data_ptr(), n_active.data_ptr(),
                                          cfg.tol, cfg.damp_above, cfg.damp_factor, ws_chol.data_ptr(),
                                          ws_chol.numel(), _stream()), "dlsa_newton_update_f64")
-        if int(n_active.item()) == 0:  # the one host read per iteration
+        left = int(n_active.item())  # the one host read per iteration
+        if left == 0:
             break
-    # final pass at the returned coefficients: Sig_inv (and the log-likelihood) for every partition
-    irls_pass(X, y, part_offsets, beta, fit_intercept, _lib.FAMILY_LOGISTIC, None, max_rows,
-              want_loglik=cfg.want_loglik, out=(g, H, ll if cfg.want_loglik else None), workspace=ws_pass)
-    passes += 1
+    # A converged partition's last step (max|delta| <= tol) is not applied by K2, so its H is already Sig_inv at the
+    # returned coefficients (dlsa/models.py:114,130): no extra pass.  Only partitions that ran out of iterations get
+    # one more pass at the coefficients they return.
+    if left > 0:
+        irls_pass(X, y, part_offsets, beta, fit_intercept, _lib.FAMILY_LOGISTIC, active, max_rows,
+                  want_loglik=False, out=(g, H, None), workspace=ws_pass, full=False)
+        passes += 1
+    if cfg.want_loglik:  # optional extra: every partition's log-likelihood at its own returned coefficients
+        irls_pass(X, y, part_offsets, beta, fit_intercept, _lib.FAMILY_LOGISTIC, None, max_rows,
+                  want_loglik=True, out=(g, H, ll), workspace=ws_pass, full=False)
+        passes += 1
     Hb = torch.empty(K, p, dtype=_F64, device=dev)
     check(lib.dlsa_batched_symv_f64(H.data_ptr(), beta.data_ptr(), K, p, Hb.data_ptr(), _stream()),
           "dlsa_batched_symv_f64")
-    return PartitionFits(coef=beta, Sig_inv=H, Sig_invMcoef=Hb, status=status, iters=iters,
-                         loglik=ll if cfg.want_loglik else None, passes=passes, n_rows=int(X.shape[0]))
+    return PartitionFits(coef=beta, Sig_inv=H, Sig_invMcoef=Hb, status=status, iters=iters, loglik=ll, passes=passes,
+                         n_rows=int(X.shape[0]))
 
 
 def fit_linear_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor) -> PartitionFits:
@@ -302,5 +311,66 @@ def dlsa_fit(X, y, part_offsets, fit_intercept=False, sample_size=None, type="la
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(n, group=group)
         sample_size = float(n.item())
+    path = lars_path(comb.Sig_inv_sum, comb.beta_byOLS, fit_intercept, sample_size, type=type)
+    return fits, comb, path
+
+
+def dlsa_fit_host(Xh: torch.Tensor, yh: torch.Tensor, part_offsets_host: torch.Tensor, fit_intercept=False,
+                  sample_size=None, type="lar", config=None, group=None, device=None, n_groups: int = 16,
+                  buffers=None):
+    """The whole hot path for HOST-resident partitions (what a Spark worker hands over: rows in host memory).
+
+    X [n, px] / y [n] float64 host tensors (pinned memory makes the copies asynchronous), ``part_offsets_host`` int64
+    [K+1] on the host.  Partitions are independent until the one-round combine, so they are cut into ``n_groups``
+    contiguous blocks: every block's host->device copy is queued up front on a copy stream, and block i is fitted on
+    the compute stream while blocks i+1.. are still crossing PCIe.  Wall time ~ copy time + one block's fit.
+    ``buffers`` = optional (X_dev, y_dev) to reuse.  Returns (fits, comb, path) like ``dlsa_fit``."""
+    if Xh.device.type != "cpu" or yh.device.type != "cpu" or part_offsets_host.device.type != "cpu":
+        raise ValueError("dlsa_fit_host takes host tensors; use dlsa_fit for device-resident data")
+    if Xh.dtype != _F64 or yh.dtype != _F64 or part_offsets_host.dtype != torch.int64:
+        raise TypeError("X, y must be float64 and part_offsets int64")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    n, px = Xh.shape
+    K = part_offsets_host.numel() - 1
+    offs = part_offsets_host.tolist()
+    if buffers is None:
+        Xd = torch.empty(n, px, dtype=_F64, device=dev)
+        yd = torch.empty(n, dtype=_F64, device=dev)
+    else:
+        Xd, yd = buffers
+    G = max(1, min(int(n_groups), K))
+    bounds = [(K * i) // G for i in range(G + 1)]
+    compute = torch.cuda.current_stream(dev)
+    copy = torch.cuda.Stream(dev)
+    copy.wait_stream(compute)  # the buffers may still be in use by earlier work on the compute stream
+    events = []
+    with torch.cuda.stream(copy):
+        for i in range(G):
+            r0, r1 = offs[bounds[i]], offs[bounds[i + 1]]
+            Xd[r0:r1].copy_(Xh[r0:r1], non_blocking=True)
+            yd[r0:r1].copy_(yh[r0:r1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            events.append(ev)
+    parts = []
+    for i in range(G):
+        k0, k1 = bounds[i], bounds[i + 1]
+        r0, r1 = offs[k0], offs[k1]
+        off_g = (part_offsets_host[k0:k1 + 1] - r0).to(dev, non_blocking=True)
+        compute.wait_event(events[i])
+        if k1 > k0:
+            parts.append(fit_logistic_partitions(Xd[r0:r1], yd[r0:r1], off_g, fit_intercept, config))
+    fits = PartitionFits(coef=torch.cat([f.coef for f in parts]), Sig_inv=torch.cat([f.Sig_inv for f in parts]),
+                         Sig_invMcoef=torch.cat([f.Sig_invMcoef for f in parts]),
+                         status=torch.cat([f.status for f in parts]), iters=torch.cat([f.iters for f in parts]),
+                         loglik=None if parts[0].loglik is None else torch.cat([f.loglik for f in parts]),
+                         passes=max(f.passes for f in parts), n_rows=int(n))
+    comb = combine_partitions(fits, group=group)
+    if sample_size is None:
+        nt = torch.tensor([float(n)], dtype=_F64, device=dev)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(nt, group=group)
+        sample_size = float(nt.item())
     path = lars_path(comb.Sig_inv_sum, comb.beta_byOLS, fit_intercept, sample_size, type=type)
     return fits, comb, path

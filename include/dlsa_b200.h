@@ -79,8 +79,11 @@ int dlsa_irls_pass_f64(const double *X, int64_t ldx, const double *y, const int6
  * K2  batched p x p Cholesky solve + Newton update for every active partition.
  * Replaces  del = solve(hess)%*%grad; damping; beta = beta + del; stop rule   dlsa/R/wlse_func.R:55-62
  *           (and sklearn's inner CG + line search, dlsa/models.py:110-113).
- *   delta = H^-1 g;  md = max|delta|;  if md > damp_above: delta *= damp_factor;  beta += delta;
- *   iters[k] += 1;  md <= tol  => active[k] = 0 (converged);  H not SPD / non-finite => status NOT_SPD, active 0.
+ *   delta = H^-1 g;  md = max|delta|;  if md > damp_above: delta *= damp_factor;
+ *   md >  tol: beta += delta, partition stays active;
+ *   md <= tol: converged, active[k] = 0 and beta is LEFT at the point H and g were evaluated at (the step is below
+ *              the solver's resolution), so H is already Sig_inv at the returned coefficients (dlsa/models.py:114,130);
+ *   iters[k] += 1;  H not SPD / non-finite => status NOT_SPD, active 0.
  *   n_active (device int, caller zeroes it) is incremented once per partition still active afterwards.
  */
 size_t dlsa_newton_update_workspace_bytes(int K, int p);

@@ -365,3 +365,53 @@ def test_linear_p100_matches_oracle(eng):
         th, Sg, Sgt, s2 = onp.ols_fit(X[off[k]:off[k + 1]], y[off[k]:off[k + 1]])
         assert np.max(np.abs(fits.coef[k].cpu().numpy() - th)) < 1e-10
         assert relfro(fits.Sig_inv[k].cpu().numpy(), Sg) < 1e-11
+
+
+def test_returned_sig_inv_is_evaluated_at_returned_coef(eng):
+    """dlsa/models.py:114,130: Sig_inv is X' diag(p(1-p)) X at the coefficients the fit RETURNS.  K2 does not apply a
+    final step below tol, so the H of the last Newton pass must equal a fresh pass at fits.coef bit for bit."""
+    g = load_golden("sim_p50_n40000_k4.npz")
+    pid, y, X, K = sim_data(g)
+    order = np.argsort(pid, kind="stable")
+    Xs, ys = X[order], y[order]
+    off = np.zeros(K + 1, dtype=np.int64)
+    off[1:] = np.cumsum(np.bincount(pid, minlength=K))
+    Xd, yd, od = dev(Xs), dev(ys), dev(off, torch.int64)
+    fits = eng.fit_logistic_partitions(Xd, yd, od)
+    assert int(fits.status.abs().sum().item()) == 0
+    _, H, _ = eng.irls_pass(Xd, yd, od, fits.coef, want_loglik=False)
+    assert torch.equal(H, fits.Sig_inv)
+    # and the returned coefficients are the MLE to well below the 1e-6 bar
+    for k in range(K):
+        c0, _, _ = onp.logistic_fit(Xs[off[k]:off[k + 1]], ys[off[k]:off[k + 1]])
+        assert np.max(np.abs(fits.coef[k].cpu().numpy() - c0)) < 1e-9
+    # optional per-partition log-likelihood at the returned coefficients
+    fl = eng.fit_logistic_partitions(Xd, yd, od, config=eng.EngineConfig(want_loglik=True))
+    assert torch.equal(fl.coef, fits.coef) and fl.passes == fits.passes + 1
+    for k in range(K):
+        ref = onp.logistic_loglik(Xs[off[k]:off[k + 1]], ys[off[k]:off[k + 1]], fits.coef[k].cpu().numpy()[:, None])
+        assert abs(fl.loglik[k].item() - float(np.ravel(ref)[0])) < 1e-8 * abs(float(np.ravel(ref)[0]))
+
+
+def test_host_entry_pipelined_blocks_match_device_entry(eng):
+    """dlsa_fit_host (host rows in, H2D copies of partition blocks overlapped with the fits of earlier blocks) must
+    give what dlsa_fit gives on the same rows already resident on the device."""
+    rng = np.random.default_rng(11)
+    sizes = rng.integers(300, 900, size=37)
+    off = ragged_offsets(sizes)
+    n, px = int(off[-1]), 12
+    X = rng.random((n, px)) - 0.5
+    beta = np.r_[np.ones(4), np.zeros(px - 4)]
+    y = (rng.random(n) < 1 / (1 + np.exp(-X @ beta))).astype(np.float64)
+    Xh, yh = torch.from_numpy(X).pin_memory(), torch.from_numpy(y).pin_memory()
+    offh = torch.from_numpy(off)
+    f0, c0, p0 = eng.dlsa_fit(dev(X), dev(y), dev(off, torch.int64), sample_size=n)
+    for groups in (1, 5, 64):
+        f1, c1, p1 = eng.dlsa_fit_host(Xh, yh, offh, sample_size=n, n_groups=groups)
+        assert torch.equal(f1.status, f0.status)
+        assert (f1.coef - f0.coef).abs().max().item() < 1e-12
+        assert relfro(f1.Sig_inv.cpu().numpy(), f0.Sig_inv.cpu().numpy()) < 1e-13
+        assert (c1.beta_byOLS - c0.beta_byOLS).abs().max().item() < 1e-12
+        assert p1.argmin_BIC == p0.argmin_BIC and torch.equal(p1.beta != 0, p0.beta != 0)
+    with pytest.raises(ValueError):
+        eng.dlsa_fit_host(dev(X), yh, offh)
