@@ -244,20 +244,31 @@ def main():
     ach_tf = n * flops_per_row / (pass_ms * 1e-3) / 1e12
     t_hbm = n * bytes_per_row / (hbm_peak * 1e9)
     t_f64 = n * flops_per_row / (f64_peak * 1e12)
-    roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                "traffic": None, "kernel": "irls_small_kernel (K1 fused Newton pass)", "peak_source": hbm_src,
-                "kernel_ms": pass_ms, "kernel_share_of_step": sum(allp) / ms,
-                "algorithmic_bytes_per_row": bytes_per_row, "algorithmic_flops_per_row": flops_per_row,
-                "fp64": {"achieved": ach_tf, "peak": f64_peak, "unit": "TFLOP/s", "frac": ach_tf / f64_peak,
-                         "peak_source": f64_src,
-                         "note": "FP64 DMMA and DFMA share one 64 FMA/clk/SM pipe on B200; at p=50 the FP64 time "
-                                 "bound exceeds the HBM time bound, so this is the binding roof"},
-                "binding_roof": "fp64" if t_f64 > t_hbm else "hbm"}
+    # The binding roof goes first.  FP64 DMMA/DFMA is the tensor-core path of this kernel (tcgen05 has no f64 kind); its
+    # peak is measured on this pool by tools/microbench_fp64.cu (MEASURED_PEAKS.json has no FP64 entry).  The HBM view
+    # (against the driver-measured copy bandwidth) is reported beside it.
+    hbm_view = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                "peak_source": hbm_src}
+    f64_view = {"bound": "tensor", "achieved": ach_tf, "peak": f64_peak, "unit": "TFLOP/s", "frac": ach_tf / f64_peak,
+                "peak_source": f64_src,
+                "note": "FP64 DMMA.8x8x4 and DFMA share one 64 FMA/clk/SM pipe on B200 (37.1 TFLOP/s measured)"}
+    binding = f64_view if t_f64 > t_hbm else hbm_view
+    roofline = dict(binding)
+    roofline.update({"traffic": None, "kernel": "irls_small_kernel (K1 fused Newton pass)" if p <= 56 else
+                     "irls_tiled_kernel (K1 fused Newton pass)",
+                     "kernel_ms": pass_ms, "kernel_share_of_step": sum(allp) / ms,
+                     "algorithmic_bytes_per_row": bytes_per_row, "algorithmic_flops_per_row": flops_per_row,
+                     "time_bound_ms": {"hbm": t_hbm * 1e3, "fp64": t_f64 * 1e3},
+                     "binding_roof": "fp64" if t_f64 > t_hbm else "hbm",
+                     "hbm": hbm_view, "fp64": f64_view})
     traffic_path = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.isfile(traffic_path):
         try:
             with open(traffic_path) as f:
-                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            if int(tj.get("p", -1)) == p:  # DRAM bytes of one launch from the committed ncu --set full capture
+                roofline["traffic"] = tj["dram_bytes_per_launch"] * (n / float(tj["rows"]))
+                roofline["traffic_source"] = "profiles/k1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
         except Exception:
             pass
 

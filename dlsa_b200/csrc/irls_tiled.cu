@@ -460,46 +460,62 @@ static TiledCfg tiled_cfg(int px, int p) {
             if (mask == 0xffu) full.push_back({m, J, mask, false});
             else part.push_back({m, J, mask, m == mg});
         }
-    // siblings: enough MMA warps for one partial block each and enough slots for everything
+    // Siblings: enough MMA warps for one partial block each and enough slots for everything.  The FP64 pipe is per
+    // sub-partition, so what has to be equal is the number of DMMAs per (sibling, sub-partition) bin: all blocks,
+    // heaviest first (full blocks, then partial ones by tile count), each to the least-loaded bin that can still take
+    // it (<= 9 blocks = 3 warps x 3 slots, <= 3 partial blocks = one per warp).  Measured with the previous deal
+    // (partial blocks first, then full ones): p=100 -> bins 27/19/26/19 tiles, the 27 set the pace (ncu: 23 % of the
+    // MMA warps' time waiting on stage barriers); this deal gives 23/23/23/22.
     const int nb = (int)(full.size() + part.size());
     c.TG = (nb + kTMma * kTNBW - 1) / (kTMma * kTNBW);
     if (c.TG < 1) c.TG = 1;
     while (c.TG * kTMma < (int)part.size()) c.TG++;
     auto heavier = [](const Blk& x, const Blk& y) { return popcount8(x.mask) > popcount8(y.mask); };
     std::stable_sort(part.begin(), part.end(), heavier);
-    const int nbins = c.TG * 4;   // (sibling, sub-partition); MMA warp w runs on sub-partition w % 4
-    std::vector<int> load(nbins, 0), npart(nbins, 0);
+    std::vector<std::vector<Blk>> bfull, bpart;
+    for (;; c.TG++) {
+        const int nbins = c.TG * 4;   // (sibling, sub-partition); MMA warp w runs on sub-partition w % 4
+        std::vector<int> load(nbins, 0);
+        bfull.assign(nbins, {});
+        bpart.assign(nbins, {});
+        bool ok = true;
+        auto place = [&](const Blk& b, bool partial) {
+            int best = -1;
+            for (int i = 0; i < nbins; i++) {
+                if ((int)(bfull[i].size() + bpart[i].size()) >= 3 * kTNBW) continue;
+                if (partial && (int)bpart[i].size() >= 3) continue;
+                if (best < 0 || load[i] < load[best]) best = i;
+            }
+            if (best < 0) { ok = false; return; }
+            (partial ? bpart : bfull)[best].push_back(b);
+            load[best] += popcount8(b.mask);
+        };
+        for (const Blk& b : full) place(b, false);
+        for (const Blk& b : part) place(b, true);
+        if (ok || c.TG >= kTMaxTG) break;
+    }
+    // inside a bin: partial blocks to distinct warps (a warp runs at most one, in its last slot), full blocks to the
+    // least-loaded warp with a free slot
     std::vector<std::vector<Blk>> wfull(c.TG * kTMma);
     std::vector<Blk> wpart(c.TG * kTMma, Blk{0, 0, 0u, false});
     std::vector<int> wload(c.TG * kTMma, 0);
-    // partial blocks, heaviest first, to the least-loaded bin that still has a warp without one
-    for (const Blk& b : part) {
-        int best = -1;
-        for (int i = 0; i < nbins; i++)
-            if (npart[i] < 3 && (best < 0 || load[i] < load[best])) best = i;
-        const int tg = best / 4, smsp = best % 4;
-        const int w = tg * kTMma + smsp + 4 * npart[best];
-        npart[best]++;
-        wpart[w] = b;
-        wload[w] += popcount8(b.mask);
-        load[best] += popcount8(b.mask);
-    }
-    // full blocks to the least-loaded bin with a free slot, inside the bin to its least-loaded warp with a free slot
-    for (const Blk& b : full) {
-        int best = -1, bestw = -1;
-        for (int i = 0; i < nbins; i++) {
-            const int tg = i / 4, smsp = i % 4;
+    for (int i = 0; i < c.TG * 4; i++) {
+        const int tg = i / 4, smsp = i % 4;
+        for (size_t t = 0; t < bpart[i].size(); t++) {
+            const int w = tg * kTMma + smsp + 4 * (int)t;
+            wpart[w] = bpart[i][t];
+            wload[w] += popcount8(bpart[i][t].mask);
+        }
+        for (const Blk& b : bfull[i]) {
             int wsel = -1;
             for (int t = 0; t < 3; t++) {
                 const int w = tg * kTMma + smsp + 4 * t;
                 const int used = (int)wfull[w].size() + (wpart[w].mask ? 1 : 0);
                 if (used < kTNBW && (wsel < 0 || wload[w] < wload[wsel])) wsel = w;
             }
-            if (wsel >= 0 && (best < 0 || load[i] < load[best])) { best = i; bestw = wsel; }
+            wfull[wsel].push_back(b);
+            wload[wsel] += 8;
         }
-        wfull[bestw].push_back(b);
-        wload[bestw] += 8;
-        load[best] += 8;
     }
     c.sched.assign((size_t)kTMaxTG * kTMma * kTNBW, 0u);
     for (int w = 0; w < c.TG * kTMma; w++) {
