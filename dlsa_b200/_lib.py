@@ -38,6 +38,9 @@ SIGNATURES = {
     "dlsa_launch_count": (C.c_ulonglong, []),
     "dlsa_irls_pass_workspace_bytes": (_sz, [_i, _i, _i64]),
     "dlsa_irls_pass_f64": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "dlsa_irls_pass_cat_workspace_bytes": (_sz, [_i, _i, _vp, _i64]),
+    "dlsa_irls_pass_cat_f64": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64,
+                                    _vp, _sz, _vp]),
     "dlsa_newton_update_workspace_bytes": (_sz, [_i, _i]),
     "dlsa_newton_update_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _vp, _sz, _vp]),
     "dlsa_spd_solve_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),

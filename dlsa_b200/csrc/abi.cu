@@ -49,6 +49,11 @@ int loglik_launch(const double*, int64_t, const double*, const int64_t*, int, in
 int onehot_launch(const double*, int, const double*, const double*, const int*, int, const int*, int64_t, double*,
                   int64_t, cudaStream_t);
 
+size_t irls_cat_workspace_bytes(int K, int n_cat, const int* n_levels, int64_t max_part_rows);
+int irls_cat_launch(const double*, int64_t, int, const double*, const double*, const int*, int, const int*, const double*,
+                    const int64_t*, int, int, const double*, const int*, double*, double*, double*, int64_t, void*,
+                    size_t, cudaStream_t);
+
 constexpr int kSmallMaxP = 56;
 
 }  // namespace dlsa
@@ -85,6 +90,32 @@ int dlsa_irls_pass_f64(const double* X, int64_t ldx, const double* y, const int6
                                  max_part_rows, workspace, workspace_bytes, st);
     return irls_tiled_launch(X, ldx, y, part_off, K, px, fit_intercept, family, beta, active, g, H, loglik,
                              max_part_rows, workspace, workspace_bytes, st);
+}
+
+size_t dlsa_irls_pass_cat_workspace_bytes(int K, int n_cat, const int* n_levels_host, int64_t max_part_rows) {
+    if (K <= 0 || n_cat <= 0 || n_cat > 8 || n_levels_host == nullptr) return 0;
+    return irls_cat_workspace_bytes(K, n_cat, n_levels_host, max_part_rows);
+}
+
+int dlsa_irls_pass_cat_f64(const double* numeric, int64_t ldn, int n_num, const double* mean, const double* std,
+                           const int* codes, int n_cat, const int* n_levels_host, const double* y,
+                           const int64_t* part_off, int K, int fit_intercept, const double* beta, const int* active,
+                           double* g, double* H, double* loglik, int64_t max_part_rows, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    DLSA_REQUIRE(K >= 0 && n_num >= 0 && ldn >= n_num && n_cat >= 0 && max_part_rows >= 0, DLSA_E_BADARG,
+                 "categorical pass: bad shape K=%d n_num=%d n_cat=%d", K, n_num, n_cat);
+    DLSA_REQUIRE(n_num <= 7 && n_cat >= 1 && n_cat <= 8, DLSA_E_UNSUPPORTED,
+                 "categorical pass: needs 1..8 categorical and at most 7 numeric columns (got %d, %d); expand with "
+                 "dlsa_onehot_expand_f64 and use dlsa_irls_pass_f64",
+                 n_cat, n_num);
+    DLSA_REQUIRE((n_num == 0 || numeric) && codes && n_levels_host && y && part_off && beta && g && H, DLSA_E_BADARG,
+                 "categorical pass: null pointer");
+    DLSA_REQUIRE((mean == nullptr) == (std == nullptr), DLSA_E_BADARG, "categorical pass: mean/std must both be given");
+    for (int c = 0; c < n_cat; ++c)
+        DLSA_REQUIRE(n_levels_host[c] >= 1, DLSA_E_BADARG, "categorical pass: column %d has %d levels", c, n_levels_host[c]);
+    if (K == 0) return 0;
+    return irls_cat_launch(numeric, ldn, n_num, mean, std, codes, n_cat, n_levels_host, y, part_off, K, fit_intercept, beta,
+                           active, g, H, loglik, max_part_rows, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 size_t dlsa_newton_update_workspace_bytes(int K, int p) { return (K <= 0 || p <= 0) ? 0 : chol_workspace_bytes(K, p); }

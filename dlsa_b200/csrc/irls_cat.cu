@@ -1,0 +1,487 @@
+// K1c — the fused Newton / IRLS pass for a design matrix with one-hot (dummy) blocks, computed from the COMPACT
+// representation [numeric columns | one integer code per categorical column] instead of the expanded dense X.
+//
+// Replaces, for the dummy branch of logistic_model (dlsa/models.py:56-91: pd.get_dummies -> dense 0/1 columns ->
+// sklearn fit -> Sig_inv = X' diag(p(1-p)) X, :130), the same quantities as dlsa_irls_pass_f64 on the expanded X:
+//   g = X'(y - prob),  H = X' diag(prob(1-prob)) X,  loglik.
+// A row of the expanded X is z = [1 | x_1..x_q] (q <= 7 numerics) plus ONE 1 per categorical column, so
+//   H[z, z]           = sum w z z'                         one DMMA per 4 rows (8x8 tile)
+//   H[level, z]       = sum_{rows at that level} w z'      DMMA with a one-hot A operand built in registers; tiles of 8
+//                                                          levels that none of the 4 rows touches are skipped
+//   H[level, level]   = H[level, 1]  (the intercept column of the block above)
+//   H[level, level']  = sum w over rows holding both       (different categorical columns) — a weighted 2-D histogram:
+//                                                          64-bit fixed-point RED.ADD into an L2-resident table
+//   g[level]          = sum r over rows at that level      same, fixed-point
+// Algorithmic traffic per row: 8 q + 4 c + 8 bytes (airline shape: 84 B instead of 1456 B), flops ~ 2*(64 + 64 c) instead of
+// p^2 + 5p.  Fixed-point sums are exact integer additions => the histogram part is bitwise independent of the order
+// in which rows arrive; resolution 2^-44 (w <= 1/4) and 2^-42 (|r| < 1) against sums of at most 2^20 rows per CTA.
+#include "common.cuh"
+
+namespace dlsa {
+
+namespace {
+
+constexpr int kCatMaxC = 8;      // categorical columns
+constexpr int kCatMaxNum = 7;    // numeric columns (z = [1 | numerics] fills one 8-wide tile)
+constexpr int kCatWarps = 8;
+constexpr int kCatStages = 4;
+constexpr int kCatThreads = kCatWarps * 32;
+constexpr int kCatMaxRowsPerCta = 1 << 20;
+constexpr double kWScale = 17592186044416.0;      // 2^44
+constexpr double kRScale = 4398046511104.0;       // 2^42
+// per-warp, per-stage shared memory: 32 rows of numerics (7 doubles), codes (8 ints), labels
+constexpr int kStageZ = 32 * kCatMaxNum * 8;
+constexpr int kStageC = 32 * kCatMaxC * 4;
+constexpr int kStageY = 32 * 8;
+constexpr int kStageBytes = kStageZ + kStageC + kStageY;  // 3072
+
+struct CatArgs {
+    const double* num;
+    int64_t ldn;
+    int n_num;
+    const int* codes;
+    int n_cat;
+    const double* mean;
+    const double* sd;
+    const double* y;
+    const int64_t* part_off;
+    int K, S;
+    int fit_intercept, want_ll;
+    const double* beta;
+    const int* active;
+    int Ltot, npairs;
+    int cat_lo[kCatMaxC + 1];            // level-space offsets of each categorical column
+    int pair_off[kCatMaxC * kCatMaxC];   // offset of the (c, c') block, c < c', in the pair table
+    double* part_d;                      // [K*S, stride_d]: Dz 64 | gz 8 | ll 1 | pad | B [NT*64]
+    unsigned long long* part_i;          // [K*S, stride_i]: gl [Lpad] | pairs [npairs]
+    int64_t stride_d, stride_i;
+    int Lpad;
+};
+
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, bool pred) {
+    const int sz = pred ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void* src, bool pred) {
+    const int sz = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, long long v) {
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// NT = 8-level tiles of the concatenated level space held in registers, NC = categorical columns compiled in.
+template <int NT, int NC>
+__global__ void __launch_bounds__(kCatThreads, 1) irls_cat_kernel(const CatArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int k = blockIdx.x / a.S;
+    const int s = blockIdx.x - k * a.S;
+    if (a.active != nullptr && a.active[k] == 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_num = a.n_num, n_cat = a.n_cat;
+
+    // shared: [warps][stages] rings | beta (8 + Lpad) | reduction buffer (NT*64 + 80)
+    unsigned char* ring = smem_raw + (size_t)warp * kCatStages * kStageBytes;
+    double* bz = reinterpret_cast<double*>(smem_raw + (size_t)kCatWarps * kCatStages * kStageBytes);
+    double* bl = bz + 8;
+    double* red = bl + a.Lpad;
+
+    // coefficients in internal order: [intercept | numerics (7) | levels]
+    {
+        const int p = a.fit_intercept + n_num + a.Ltot;
+        const double* bk = a.beta + (size_t)k * p;
+        for (int i = threadIdx.x; i < 8 + a.Lpad; i += kCatThreads) {
+            double v = 0.0;
+            if (i == 0) v = a.fit_intercept ? bk[0] : 0.0;
+            else if (i < 8) v = (i - 1 < n_num) ? bk[a.fit_intercept + i - 1] : 0.0;
+            else if (i - 8 < a.Ltot) v = bk[a.fit_intercept + n_num + (i - 8)];
+            bz[i] = v;
+        }
+    }
+    __syncthreads();
+
+    // this CTA's rows: slice s of partition k, in 32-row groups dealt round-robin to the warps
+    const int64_t p0 = a.part_off[k], p1 = a.part_off[k + 1];
+    const int64_t rows = p1 - p0;
+    const int64_t per = ((rows + a.S - 1) / a.S + 31) / 32 * 32;
+    const int64_t r0 = p0 + (int64_t)s * per;
+    const int64_t r1 = (r0 + per < p1) ? r0 + per : p1;
+    const int64_t ngroups = r1 > r0 ? (r1 - r0 + 31) / 32 : 0;
+    const int64_t my_groups = ngroups > warp ? (ngroups - warp + kCatWarps - 1) / kCatWarps : 0;
+
+    unsigned long long* gl = a.part_i + (size_t)blockIdx.x * a.stride_i;
+    unsigned long long* pairs = gl + a.Lpad;
+
+    auto issue = [&](int64_t gi) {  // cp.async the gi-th group of this warp into stage gi % kCatStages
+        if (gi < my_groups) {
+            const int64_t R0 = r0 + (warp + gi * kCatWarps) * 32;
+            const int nv = (int)((r1 - R0 < 32) ? (r1 - R0) : 32);
+            unsigned char* st = ring + (size_t)(gi % kCatStages) * kStageBytes;
+            const uint32_t zs = smem_u32(st), cs = zs + kStageZ, ys = cs + kStageC;
+            if (a.ldn == n_num) {
+                const double* src = a.num + R0 * n_num;
+                for (int i = 0; i < n_num; ++i) {
+                    const int e = lane + 32 * i;
+                    const bool ok = e < nv * n_num;
+                    cp_async8_zfill(zs + 8 * e, src + (ok ? e : 0), ok);
+                }
+            } else {
+                for (int i = 0; i < n_num; ++i) {
+                    const int e = lane + 32 * i;
+                    const int rr = e / n_num, cc = e - rr * n_num;
+                    const bool ok = rr < nv;
+                    cp_async8_zfill(zs + 8 * e, a.num + (R0 + (ok ? rr : 0)) * a.ldn + cc, ok);
+                }
+            }
+            const int* csrc = a.codes + R0 * n_cat;
+            for (int i = 0; i < n_cat; ++i) {
+                const int e = lane + 32 * i;
+                const bool ok = e < nv * n_cat;
+                cp_async4_zfill(cs + 4 * e, csrc + (ok ? e : 0), ok);
+            }
+            cp_async8_zfill(ys + 8 * lane, a.y + R0 + (lane < nv ? lane : 0), lane < nv);
+        }
+        cp_async_commit();  // one (possibly empty) group per call keeps the wait_group arithmetic uniform
+    };
+
+    double acc[2 * NT];
+#pragma unroll
+    for (int i = 0; i < 2 * NT; ++i) acc[i] = 0.0;
+    double dz0 = 0.0, dz1 = 0.0, ll = 0.0;
+    double gz[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gz[j] = 0.0;
+
+    for (int64_t gi = 0; gi < kCatStages - 1; ++gi) issue(gi);
+
+    const int jcol = lane >> 2;  // the z column / level-within-tile this lane holds in the MMA fragments
+    for (int64_t gi = 0; gi < my_groups; ++gi) {
+        issue(gi + kCatStages - 1);
+        cp_async_wait<kCatStages - 1>();
+        __syncwarp();
+        const int64_t R0 = r0 + (warp + gi * kCatWarps) * 32;
+        const int nv = (int)((r1 - R0 < 32) ? (r1 - R0) : 32);
+        unsigned char* st = ring + (size_t)(gi % kCatStages) * kStageBytes;
+        double* zs = reinterpret_cast<double*>(st);
+        const int* cs = reinterpret_cast<const int*>(st + kStageZ);
+        const double* ys = reinterpret_cast<const double*>(st + kStageZ + kStageC);
+
+        // ---- row stage: lane = row -----------------------------------------------------------------------
+        const bool valid = lane < nv;
+        double eta = bz[0];
+        double z[kCatMaxNum];
+#pragma unroll
+        for (int j = 0; j < kCatMaxNum; ++j) {
+            z[j] = 0.0;
+            if (j < n_num) {
+                double v = zs[lane * n_num + j];
+                if (a.mean != nullptr) {  // dlsa/models.py:99-101, same expression as dlsa_onehot_expand_f64
+                    v = (v - a.mean[j]) / a.sd[j];
+                    zs[lane * n_num + j] = v;
+                }
+                z[j] = v;
+                eta = fma(v, bz[1 + j], eta);
+            }
+        }
+        int lev[NC];
+        uint32_t plo = 0xFFFFFFFFu, phi = 0xFFFFFFFFu;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            lev[c] = -1;
+            if (c < n_cat && valid) {
+                const int code = cs[lane * n_cat + c];
+                if (code >= 0) {
+                    lev[c] = a.cat_lo[c] + code;
+                    eta += bl[lev[c]];
+                }
+            }
+            const uint32_t byte = (uint32_t)(lev[c] & 0xFF);
+            if (c < 4) plo = (plo & ~(0xFFu << (8 * c))) | (byte << (8 * c));
+            else phi = (phi & ~(0xFFu << (8 * (c - 4)))) | (byte << (8 * (c - 4)));
+        }
+        double w = 0.0, r = 0.0;
+        if (valid) {
+            const double yy = ys[lane];
+            const double prob = sigmoid_f64(eta);
+            w = prob * (1.0 - prob);
+            r = yy - prob;
+            if (a.want_ll) ll += yy * eta - log1pexp_f64(eta);
+        }
+        gz[0] += r;
+#pragma unroll
+        for (int j = 0; j < kCatMaxNum; ++j) gz[1 + j] = fma(r, z[j], gz[1 + j]);
+        {
+            const long long wfix = __double2ll_rn(w * kWScale);
+            const long long rfix = __double2ll_rn(r * kRScale);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                if (lev[c] >= 0) {
+                    red_add_u64(gl + lev[c], rfix);
+#pragma unroll
+                    for (int d = c + 1; d < NC; ++d)
+                        if (lev[d] >= 0)
+                            red_add_u64(pairs + a.pair_off[c * kCatMaxC + d] +
+                                            (lev[c] - a.cat_lo[c]) * (a.cat_lo[d + 1] - a.cat_lo[d]) +
+                                            (lev[d] - a.cat_lo[d]),
+                                        wfix);
+                }
+            }
+        }
+        if (a.mean != nullptr) __syncwarp();
+
+        // ---- MMA stage: 8 k-steps of 4 rows ------------------------------------------------------------------
+#pragma unroll 2
+        for (int ks = 0; ks < 8; ++ks) {
+            const int src = 4 * ks + (lane & 3);
+            const double wk = __shfl_sync(0xffffffffu, w, src);
+            const uint32_t qlo = __shfl_sync(0xffffffffu, plo, src);
+            uint32_t qhi = 0xFFFFFFFFu;
+            if (NC > 4) qhi = __shfl_sync(0xffffffffu, phi, src);
+            double zz = 1.0;
+            if (jcol > 0) zz = (jcol - 1 < n_num) ? zs[src * n_num + jcol - 1] : 0.0;
+            const double b = wk * zz;
+            dmma884(dz0, dz1, zz, b);
+            uint32_t mine = 0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const uint32_t lv = ((c < 4 ? qlo : qhi) >> (8 * (c & 3))) & 0xFFu;
+                if ((int)(lv & 7u) == jcol) mine |= 1u << (lv >> 3);  // lv = 0xFF (no level) sets bit 31: never a tile
+            }
+            const uint32_t hit = __reduce_or_sync(0xffffffffu, mine);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                if ((hit >> t) & 1u) {
+                    const double av = __hiloint2double((int)(((mine >> t) & 1u) * 0x3FF00000u), 0);
+                    dmma884(acc[2 * t], acc[2 * t + 1], av, b);
+                }
+            }
+        }
+        __syncwarp();  // the stage is re-filled by the next issue()
+    }
+    cp_async_wait<0>();
+
+    // ---- CTA reduction in a fixed warp order, then the partial goes to the workspace ---------------------------
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) gz[j] += shfl_xor_f64(gz[j], m);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) ll += shfl_xor_f64(ll, m);
+    const int di = lane >> 2, dj = 2 * (lane & 3);
+    for (int wv = 0; wv < kCatWarps; ++wv) {
+        if (warp == wv) {
+            const bool first = wv == 0;
+            // red: Dz [64] | gz [8] | ll | pad to 80 | B tiles [NT][8][8]
+            red[di * 8 + dj] = (first ? 0.0 : red[di * 8 + dj]) + dz0;
+            red[di * 8 + dj + 1] = (first ? 0.0 : red[di * 8 + dj + 1]) + dz1;
+            if (lane < 8) {
+                double v = gz[0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) v = (lane == j) ? gz[j] : v;
+                red[64 + lane] = (first ? 0.0 : red[64 + lane]) + v;
+            }
+            if (lane == 8) red[72] = (first ? 0.0 : red[72]) + ll;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                double* o = red + 80 + t * 64 + di * 8 + dj;
+                o[0] = (first ? 0.0 : o[0]) + acc[2 * t];
+                o[1] = (first ? 0.0 : o[1]) + acc[2 * t + 1];
+            }
+        }
+        __syncthreads();
+    }
+    double* out = a.part_d + (size_t)blockIdx.x * a.stride_d;
+    for (int i = threadIdx.x; i < 80 + NT * 64; i += kCatThreads) out[i] = red[i];
+}
+
+// Assemble the full symmetric H [p, p], g [p] and loglik of every active partition from its S partials, slices summed in a
+// fixed order.  Output order = the expanded design: [intercept] numerics, then the level columns (dlsa/models.py:71-79).
+__global__ void irls_cat_finalize_kernel(const CatArgs a, double* __restrict__ g, double* __restrict__ H,
+                                         double* __restrict__ loglik) {
+    const int k = blockIdx.x;
+    if (a.active != nullptr && a.active[k] == 0) return;
+    const int q = a.n_num, ic = a.fit_intercept;
+    const int p = ic + q + a.Ltot;
+    const double* pd = a.part_d + (size_t)k * a.S * a.stride_d;
+    const unsigned long long* pi = a.part_i + (size_t)k * a.S * a.stride_i;
+    auto internal = [&](int o) {  // output coefficient index -> internal index (0 = intercept, 1..7 numerics, 8.. levels)
+        if (ic) {
+            if (o == 0) return 0;
+            return (o - 1 < q) ? o : 8 + (o - 1 - q);
+        }
+        return (o < q) ? o + 1 : 8 + (o - q);
+    };
+    auto cat_of = [&](int level) {
+        int c = 0;
+        while (c + 1 < a.n_cat && level >= a.cat_lo[c + 1]) ++c;
+        return c;
+    };
+    double* Hk = H + (size_t)k * p * p;
+    for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
+        const int o1 = e / p, o2 = e - o1 * p;
+        if (o2 > o1) continue;
+        int u1 = internal(o1), u2 = internal(o2);
+        if (u1 > u2) { const int t = u1; u1 = u2; u2 = t; }
+        double v = 0.0;
+        if (u2 < 8) {
+            for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + u1 * 8 + u2];
+        } else if (u1 < 8) {
+            for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + 80 + (u2 - 8) * 8 + u1];
+        } else {
+            const int l1 = u1 - 8, l2 = u2 - 8;
+            if (l1 == l2) {
+                for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + 80 + l1 * 8];
+            } else {
+                const int c1 = cat_of(l1), c2 = cat_of(l2);
+                if (c1 != c2) {
+                    const int idx = a.pair_off[c1 * kCatMaxC + c2] + (l1 - a.cat_lo[c1]) * (a.cat_lo[c2 + 1] - a.cat_lo[c2]) +
+                                    (l2 - a.cat_lo[c2]);
+                    for (int sl = 0; sl < a.S; ++sl)  // per-slice conversion: a slice sum is < 2^63, the partition sum may not be
+                        v += (double)(long long)pi[sl * a.stride_i + a.Lpad + idx] * (1.0 / kWScale);
+                }
+            }
+        }
+        Hk[o1 * p + o2] = v;
+        Hk[o2 * p + o1] = v;
+    }
+    for (int o = threadIdx.x; o < p; o += blockDim.x) {
+        const int u = internal(o);
+        double v = 0.0;
+        if (u < 8) {
+            for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + 64 + u];
+        } else {
+            for (int sl = 0; sl < a.S; ++sl) v += (double)(long long)pi[sl * a.stride_i + (u - 8)] * (1.0 / kRScale);
+        }
+        g[(size_t)k * p + o] = v;
+    }
+    if (loglik != nullptr && threadIdx.x == 0) {
+        double v = 0.0;
+        for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + 72];
+        loglik[k] = v;
+    }
+}
+
+struct CatPlan {
+    int Ltot, Lpad, NT, NTb, npairs, S;
+    int64_t stride_d, stride_i;
+    size_t bytes_d, bytes_i;
+};
+
+int cat_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+
+bool cat_plan(int K, int n_cat, const int* n_levels, int64_t max_part_rows, CatPlan& pl) {
+    pl.Ltot = 0;
+    pl.npairs = 0;
+    for (int c = 0; c < n_cat; ++c) {
+        pl.npairs += pl.Ltot * n_levels[c];  // every earlier level x this column's levels
+        pl.Ltot += n_levels[c];
+    }
+    pl.NT = (pl.Ltot + 7) / 8;
+    pl.Lpad = pl.NT * 8;
+    pl.NTb = pl.NT <= 8 ? 8 : (pl.NT <= 16 ? 16 : 24);  // the register-tile bucket the kernel is compiled for
+    const int sms = cat_sm_count();
+    int64_t S = K < sms ? sms / K : 1;
+    const int64_t s_rows = (max_part_rows + 2047) / 2048;  // at least 2048 rows per CTA
+    if (S > s_rows) S = s_rows;
+    const int64_t s_min = (max_part_rows + kCatMaxRowsPerCta - 1) / kCatMaxRowsPerCta;  // fixed-point headroom
+    if (S < s_min) S = s_min;
+    if (S < 1) S = 1;
+    pl.S = (int)S;
+    pl.stride_d = 80 + (int64_t)pl.NTb * 64;
+    pl.stride_i = pl.Lpad + pl.npairs;
+    pl.bytes_d = (size_t)K * S * pl.stride_d * 8;
+    pl.bytes_i = (size_t)K * S * pl.stride_i * 8;
+    return true;
+}
+
+}  // namespace
+
+size_t irls_cat_workspace_bytes(int K, int n_cat, const int* n_levels, int64_t max_part_rows) {
+    CatPlan pl;
+    cat_plan(K, n_cat, n_levels, max_part_rows, pl);
+    return pl.bytes_d + pl.bytes_i + 256;
+}
+
+template <int NT, int NC>
+static int cat_launch_t(const CatArgs& a, size_t smem, cudaStream_t st) {
+    auto kern = irls_cat_kernel<NT, NC>;
+    DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<a.K * a.S, kCatThreads, smem, st>>>(a);
+    count_launch();
+    return check_launch("irls_cat_kernel");
+}
+
+int irls_cat_launch(const double* numeric, int64_t ldn, int n_num, const double* mean, const double* sd, const int* codes,
+                    int n_cat, const int* n_levels, const double* y, const int64_t* part_off, int K, int fit_intercept,
+                    const double* beta, const int* active, double* g, double* H, double* loglik, int64_t max_part_rows,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    CatPlan pl;
+    cat_plan(K, n_cat, n_levels, max_part_rows, pl);
+    DLSA_REQUIRE(pl.NT <= 24, DLSA_E_UNSUPPORTED, "categorical pass: %d levels in total (max 192)", pl.Ltot);
+    const size_t need = pl.bytes_d + pl.bytes_i + 256;
+    DLSA_REQUIRE(workspace != nullptr && workspace_bytes >= need, DLSA_E_WORKSPACE,
+                 "categorical pass: workspace %zu < %zu bytes", workspace_bytes, need);
+    CatArgs a{};
+    a.num = numeric;
+    a.ldn = ldn;
+    a.n_num = n_num;
+    a.codes = codes;
+    a.n_cat = n_cat;
+    a.mean = mean;
+    a.sd = sd;
+    a.y = y;
+    a.part_off = part_off;
+    a.K = K;
+    a.S = pl.S;
+    a.fit_intercept = fit_intercept ? 1 : 0;
+    a.want_ll = loglik != nullptr;
+    a.beta = beta;
+    a.active = active;
+    a.Ltot = pl.Ltot;
+    a.Lpad = pl.Lpad;
+    a.npairs = pl.npairs;
+    int lo = 0, off = 0;
+    for (int c = 0; c < n_cat; ++c) {
+        a.cat_lo[c] = lo;
+        for (int d = 0; d < c; ++d) {
+            a.pair_off[d * kCatMaxC + c] = off;
+            off += n_levels[d] * n_levels[c];
+        }
+        lo += n_levels[c];
+    }
+    for (int c = n_cat; c <= kCatMaxC; ++c) a.cat_lo[c] = lo;
+    const uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+    a.part_d = reinterpret_cast<double*>(base);
+    a.part_i = reinterpret_cast<unsigned long long*>(base + pl.bytes_d);
+    a.stride_d = pl.stride_d;
+    a.stride_i = pl.stride_i;
+    DLSA_CUDA(cudaMemsetAsync(a.part_i, 0, pl.bytes_i, st));
+    const int NTb = pl.NTb;
+    const size_t smem = (size_t)kCatWarps * kCatStages * kStageBytes + (size_t)(8 + pl.Lpad + 80 + NTb * 64) * 8;
+    int rc;
+    const bool c4 = n_cat <= 4;
+    if (NTb == 8) rc = c4 ? cat_launch_t<8, 4>(a, smem, st) : cat_launch_t<8, 8>(a, smem, st);
+    else if (NTb == 16) rc = c4 ? cat_launch_t<16, 4>(a, smem, st) : cat_launch_t<16, 8>(a, smem, st);
+    else rc = c4 ? cat_launch_t<24, 4>(a, smem, st) : cat_launch_t<24, 8>(a, smem, st);
+    if (rc != 0) return rc;
+    irls_cat_finalize_kernel<<<K, 256, 0, st>>>(a, g, H, loglik);
+    count_launch();
+    return check_launch("irls_cat_finalize_kernel");
+}
+
+}  // namespace dlsa

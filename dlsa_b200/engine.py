@@ -136,6 +136,48 @@ def irls_pass(X, y, part_offsets, beta, fit_intercept=False, family=_lib.FAMILY_
     return g, H, ll
 
 
+def _newton_fit(pass_fn, K: int, p: int, dev, cfg: EngineConfig, n_rows: int, beta_init=None) -> PartitionFits:
+    """The lock-step Newton loop shared by the dense and the categorical map: ``pass_fn(beta, active, out, want_loglik,
+    full)`` launches one fused pass (K1 / K1c) into ``out = (g, H, ll)``; K2 updates every active partition."""
+    beta = torch.zeros(K, p, dtype=_F64, device=dev) if beta_init is None else beta_init.to(dev, _F64).clone()
+    g = torch.zeros(K, p, dtype=_F64, device=dev)
+    H = torch.zeros(K, p, p, dtype=_F64, device=dev)
+    ll = torch.zeros(K, dtype=_F64, device=dev) if cfg.want_loglik else None
+    status = torch.full((K,), _lib.ST_NOT_CONVERGED, dtype=torch.int32, device=dev)
+    active = torch.ones(K, dtype=torch.int32, device=dev)
+    iters = torch.zeros(K, dtype=torch.int32, device=dev)
+    n_active = torch.zeros(1, dtype=torch.int32, device=dev)
+    max_delta = torch.zeros(K, dtype=_F64, device=dev)
+    ws_chol = _workspace(lib.dlsa_newton_update_workspace_bytes(K, p), dev)
+    passes = 0
+    left = K
+    for _ in range(cfg.max_iter):
+        pass_fn(beta, active, (g, H, None), False, left == K)
+        passes += 1
+        n_active.zero_()
+        check(lib.dlsa_newton_update_f64(H.data_ptr(), g.data_ptr(), K, p, beta.data_ptr(), max_delta.data_ptr(),
+                                         status.data_ptr(), active.data_ptr(), iters.data_ptr(), n_active.data_ptr(),
+                                         cfg.tol, cfg.damp_above, cfg.damp_factor, ws_chol.data_ptr(),
+                                         ws_chol.numel(), _stream()), "dlsa_newton_update_f64")
+        left = int(n_active.item())  # the one host read per iteration
+        if left == 0:
+            break
+    # A converged partition's last step (max|delta| <= tol) is not applied by K2, so its H is already Sig_inv at the
+    # returned coefficients (dlsa/models.py:114,130): no extra pass.  Only partitions that ran out of iterations get
+    # one more pass at the coefficients they return.
+    if left > 0:
+        pass_fn(beta, active, (g, H, None), False, False)
+        passes += 1
+    if cfg.want_loglik:  # optional extra: every partition's log-likelihood at its own returned coefficients
+        pass_fn(beta, None, (g, H, ll), True, False)
+        passes += 1
+    Hb = torch.empty(K, p, dtype=_F64, device=dev)
+    check(lib.dlsa_batched_symv_f64(H.data_ptr(), beta.data_ptr(), K, p, Hb.data_ptr(), _stream()),
+          "dlsa_batched_symv_f64")
+    return PartitionFits(coef=beta, Sig_inv=H, Sig_invMcoef=Hb, status=status, iters=iters, loglik=ll, passes=passes,
+                         n_rows=n_rows)
+
+
 def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor, fit_intercept: bool = False,
                             config: Optional[EngineConfig] = None, beta_init: Optional[torch.Tensor] = None
                             ) -> PartitionFits:
@@ -153,47 +195,101 @@ def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torc
     p = px + (1 if fit_intercept else 0)
     sizes = part_offsets[1:] - part_offsets[:-1]
     max_rows = int(sizes.max().item()) if K > 0 else 0
-    beta = torch.zeros(K, p, dtype=_F64, device=dev) if beta_init is None else beta_init.to(dev, _F64).clone()
-    g = torch.zeros(K, p, dtype=_F64, device=dev)
-    H = torch.zeros(K, p, p, dtype=_F64, device=dev)
-    ll = torch.zeros(K, dtype=_F64, device=dev) if cfg.want_loglik else None
-    status = torch.full((K,), _lib.ST_NOT_CONVERGED, dtype=torch.int32, device=dev)
-    active = torch.ones(K, dtype=torch.int32, device=dev)
-    iters = torch.zeros(K, dtype=torch.int32, device=dev)
-    n_active = torch.zeros(1, dtype=torch.int32, device=dev)
-    max_delta = torch.zeros(K, dtype=_F64, device=dev)
     ws_pass = _workspace(lib.dlsa_irls_pass_workspace_bytes(K, p, max_rows), dev)
-    ws_chol = _workspace(lib.dlsa_newton_update_workspace_bytes(K, p), dev)
-    passes = 0
-    left = K
-    for _ in range(cfg.max_iter):
+
+    def pass_fn(beta, active, out, want_ll, full):
         irls_pass(X, y, part_offsets, beta, fit_intercept, _lib.FAMILY_LOGISTIC, active, max_rows,
-                  want_loglik=False, out=(g, H, None), workspace=ws_pass, full=(left == K))
-        passes += 1
-        n_active.zero_()
-        check(lib.dlsa_newton_update_f64(H.data_ptr(), g.data_ptr(), K, p, beta.data_ptr(), max_delta.data_ptr(),
-                                         status.data_ptr(), active.data_ptr(), iters.data_ptr(), n_active.data_ptr(),
-                                         cfg.tol, cfg.damp_above, cfg.damp_factor, ws_chol.data_ptr(),
-                                         ws_chol.numel(), _stream()), "dlsa_newton_update_f64")
-        left = int(n_active.item())  # the one host read per iteration
-        if left == 0:
-            break
-    # A converged partition's last step (max|delta| <= tol) is not applied by K2, so its H is already Sig_inv at the
-    # returned coefficients (dlsa/models.py:114,130): no extra pass.  Only partitions that ran out of iterations get
-    # one more pass at the coefficients they return.
-    if left > 0:
-        irls_pass(X, y, part_offsets, beta, fit_intercept, _lib.FAMILY_LOGISTIC, active, max_rows,
-                  want_loglik=False, out=(g, H, None), workspace=ws_pass, full=False)
-        passes += 1
-    if cfg.want_loglik:  # optional extra: every partition's log-likelihood at its own returned coefficients
-        irls_pass(X, y, part_offsets, beta, fit_intercept, _lib.FAMILY_LOGISTIC, None, max_rows,
-                  want_loglik=True, out=(g, H, ll), workspace=ws_pass, full=False)
-        passes += 1
-    Hb = torch.empty(K, p, dtype=_F64, device=dev)
-    check(lib.dlsa_batched_symv_f64(H.data_ptr(), beta.data_ptr(), K, p, Hb.data_ptr(), _stream()),
-          "dlsa_batched_symv_f64")
-    return PartitionFits(coef=beta, Sig_inv=H, Sig_invMcoef=Hb, status=status, iters=iters, loglik=ll, passes=passes,
-                         n_rows=int(X.shape[0]))
+                  want_loglik=want_ll, out=out, workspace=ws_pass, full=full)
+
+    return _newton_fit(pass_fn, K, p, dev, cfg, int(X.shape[0]), beta_init)
+
+
+def _check_cat_inputs(numeric, codes, n_levels, y, part_offsets):
+    dev = _require_cuda(codes, y, part_offsets)
+    n_levels = [int(v) for v in n_levels]
+    if codes.dtype != torch.int32 or codes.dim() != 2 or not codes.is_contiguous() or codes.shape[1] != len(n_levels):
+        raise TypeError("codes must be a contiguous int32 [n, n_cat] tensor with one column per entry of n_levels")
+    n = codes.shape[0]
+    if numeric is None:
+        n_num = 0
+    else:
+        _require_cuda(numeric, codes)
+        if numeric.dtype != _F64 or numeric.dim() != 2 or numeric.shape[0] != n or (numeric.shape[1] and numeric.stride(1) != 1):
+            raise TypeError("numeric must be float64 [n, n_num] row-major")
+        n_num = numeric.shape[1]
+    if y.dtype != _F64 or y.numel() != n:
+        raise TypeError("y must be float64 [n]")
+    if part_offsets.dtype != torch.int64 or part_offsets.dim() != 1 or part_offsets.numel() < 1:
+        raise TypeError("part_offsets must be int64 [K+1]")
+    return dev, y.contiguous().view(-1), n_levels, n_num
+
+
+def irls_pass_cat(numeric, codes, n_levels, y, part_offsets, beta, fit_intercept=False, mean=None, std=None, active=None,
+                  max_part_rows=None, want_loglik=True, out=None, workspace=None, full=None):
+    """One fused pass over the COMPACT design [numeric | categorical codes] (K1c, ``dlsa_irls_pass_cat_f64``): the
+    (g, H, loglik) of ``irls_pass`` on the one-hot expanded matrix, without materialising it.
+    ``codes[i, c]`` in [0, n_levels[c]) or -1 for a baseline level; columns = [intercept] numerics, then each
+    categorical's levels (dlsa/models.py:71-79)."""
+    dev, y, n_levels, n_num = _check_cat_inputs(numeric, codes, n_levels, y, part_offsets)
+    K = part_offsets.numel() - 1
+    p = int(fit_intercept) + n_num + sum(n_levels)
+    if max_part_rows is None:
+        max_part_rows = int((part_offsets[1:] - part_offsets[:-1]).max().item()) if K > 0 else 0
+    if out is None:
+        g = torch.zeros(K, p, dtype=_F64, device=dev)
+        H = torch.zeros(K, p, p, dtype=_F64, device=dev)
+        ll = torch.zeros(K, dtype=_F64, device=dev) if want_loglik else None
+    else:
+        g, H, ll = out
+    import ctypes as C
+    nl = (C.c_int * len(n_levels))(*n_levels)
+    need = lib.dlsa_irls_pass_cat_workspace_bytes(K, len(n_levels), nl, max_part_rows)
+    if workspace is None or workspace.numel() < need:
+        workspace = _workspace(need, dev)
+    if PASS_EVENTS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(lib.dlsa_irls_pass_cat_f64(_ptr(numeric) if n_num else None, numeric.stride(0) if n_num else 0, n_num,
+                                     _ptr(mean), _ptr(std), codes.data_ptr(), len(n_levels), nl, y.data_ptr(),
+                                     part_offsets.data_ptr(), K, int(fit_intercept), beta.data_ptr(), _ptr(active),
+                                     g.data_ptr(), H.data_ptr(), _ptr(ll), max_part_rows, workspace.data_ptr(),
+                                     workspace.numel(), _stream()), "dlsa_irls_pass_cat_f64")
+    if PASS_EVENTS is not None:
+        e1.record()
+        PASS_EVENTS.append((e0, e1, (active is None) if full is None else bool(full)))
+    return g, H, ll
+
+
+def cat_supported(n_num: int, n_levels) -> bool:
+    """Shape limits of the compact pass (include/dlsa_b200.h, K1c); outside them expand and use the dense pass."""
+    n_levels = list(n_levels)
+    return n_num <= 7 and 1 <= len(n_levels) <= 8 and sum(n_levels) <= 192 and min(n_levels) >= 1
+
+
+def fit_logistic_partitions_cat(numeric, codes, n_levels, y, part_offsets, fit_intercept: bool = False, mean=None,
+                                std=None, config: Optional[EngineConfig] = None,
+                                beta_init: Optional[torch.Tensor] = None) -> PartitionFits:
+    """``fit_logistic_partitions`` for a design with dummy blocks kept compact: numeric [n, n_num] float64 (optionally
+    standardised on load with mean/std, dlsa/models.py:99-101) and codes [n, n_cat] int32.  Same outputs, same column
+    order as fitting the one-hot expanded matrix (the dummy branch of logistic_model, dlsa/models.py:56-91)."""
+    cfg = config or EngineConfig()
+    dev, y, n_levels, n_num = _check_cat_inputs(numeric, codes, n_levels, y, part_offsets)
+    K = part_offsets.numel() - 1
+    p = int(fit_intercept) + n_num + sum(n_levels)
+    sizes = part_offsets[1:] - part_offsets[:-1]
+    max_rows = int(sizes.max().item()) if K > 0 else 0
+    import ctypes as C
+    nl = (C.c_int * len(n_levels))(*n_levels)
+    ws_pass = _workspace(lib.dlsa_irls_pass_cat_workspace_bytes(K, len(n_levels), nl, max_rows), dev)
+    if mean is not None:
+        mean = mean.to(dev, _F64).contiguous()
+        std = std.to(dev, _F64).contiguous()
+
+    def pass_fn(beta, active, out, want_ll, full):
+        irls_pass_cat(numeric, codes, n_levels, y, part_offsets, beta, fit_intercept, mean, std, active, max_rows,
+                      want_loglik=want_ll, out=out, workspace=ws_pass, full=full)
+
+    return _newton_fit(pass_fn, K, p, dev, cfg, int(codes.shape[0]), beta_init)
 
 
 def fit_linear_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor) -> PartitionFits:

@@ -76,3 +76,56 @@ def group_by_partition(X: torch.Tensor, y: torch.Tensor, partition_id: torch.Ten
     off = torch.zeros(K + 1, dtype=torch.int64, device=X.device)
     off[1:] = torch.cumsum(counts, 0)
     return X[order].contiguous(), y[order].contiguous(), off
+
+
+# ---- airline-shaped synthetic design (BASELINE.json configs[2]; SURVEY.md §8d "C3") ---------------------------------
+# 7 standardised numerics ~N(0,1) (Year, DayofMonth, DepTime, CRSDepTime, CRSArrTime, ActualElapsedTime, Distance) and
+# the categoricals Month(12), DayOfWeek(7), UniqueCarrier(8 incl. OTHERS), Origin(76), Dest(76); the first level of each
+# is the baseline (projects/logistic_dlsa.py:157-165) => 11+6+7+75+75 = 174 dummy columns, p = 182 with the intercept.
+AIRLINE_LEVELS = (12, 7, 8, 76, 76)
+AIRLINE_ZIPF = (False, False, True, True, True)
+AIRLINE_NUM = 7
+
+
+def airline_truth(seed: int = 11):
+    """(beta0, beta_num [7], beta_levels [174]): N(0, 0.3^2) with 60 % zeros, intercept -1."""
+    rng = np.random.default_rng(seed)
+    p = AIRLINE_NUM + sum(L - 1 for L in AIRLINE_LEVELS)
+    b = rng.standard_normal(p) * 0.3
+    b[rng.random(p) < 0.6] = 0.0
+    return -1.0, b[:AIRLINE_NUM].copy(), b[AIRLINE_NUM:].copy()
+
+
+def airline_shaped_device(n: int, seed: int, device, chunk: int = 4_000_000):
+    """Compact airline-shaped design on ``device``: numeric [n,7] float64, codes [n,5] int32 (level-in-block index, -1 =
+    baseline level), n_levels (11,6,7,75,75), y [n] ~ Bernoulli(sigmoid(eta)).  torch's generator does the sampling
+    (benchmark input, not part of the hot path)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    b0, bnum, blev = airline_truth()
+    bnum_d = torch.as_tensor(bnum, device=device)
+    n_levels = [L - 1 for L in AIRLINE_LEVELS]
+    base = np.concatenate([[0], np.cumsum(n_levels)])
+    blev_d = torch.as_tensor(np.concatenate([blev, [0.0]]), device=device)  # slot -1 -> 0 for the baseline level
+    numeric = torch.empty(n, AIRLINE_NUM, dtype=torch.float64, device=device)
+    codes = torch.empty(n, len(n_levels), dtype=torch.int32, device=device)
+    y = torch.empty(n, dtype=torch.float64, device=device)
+    cdfs = []
+    for L, zipf in zip(AIRLINE_LEVELS, AIRLINE_ZIPF):
+        w = 1.0 / np.arange(1, L + 1) if zipf else np.ones(L)
+        cdfs.append(torch.as_tensor(np.cumsum(w / w.sum()), device=device))
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        num = torch.randn(m, AIRLINE_NUM, dtype=torch.float64, device=device, generator=gen)
+        eta = num @ bnum_d + b0
+        for c, cdf in enumerate(cdfs):
+            u = torch.rand(m, dtype=torch.float64, device=device, generator=gen)
+            lvl = torch.searchsorted(cdf, u).clamp_(max=AIRLINE_LEVELS[c] - 1)  # 0 = baseline (the most frequent level)
+            code = (lvl - 1).to(torch.int32)
+            codes[s:s + m, c] = code
+            idx = torch.where(code >= 0, code.to(torch.int64) + int(base[c]), torch.full_like(lvl, blev_d.numel() - 1))
+            eta += blev_d[idx]
+        u = torch.rand(m, dtype=torch.float64, device=device, generator=gen)
+        y[s:s + m] = (u < torch.sigmoid(eta)).to(torch.float64)
+        numeric[s:s + m] = num
+    return numeric, codes, n_levels, y

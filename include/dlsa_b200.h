@@ -76,6 +76,29 @@ int dlsa_irls_pass_f64(const double *X, int64_t ldx, const double *y, const int6
                        double *loglik, int64_t max_part_rows, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K1c the same fused pass for a design with one-hot (dummy) blocks, computed from the COMPACT representation
+ *     [numeric | one code per categorical column] — the expanded 0/1 columns are never materialised.
+ * Replaces the dummy branch of logistic_model: pd.get_dummies(sparse=True) -> dense design -> fit -> Sig_inv
+ *                                                                            dlsa/models.py:56-91,110-114,130
+ * Outputs are those of dlsa_irls_pass_f64 on the matrix dlsa_onehot_expand_f64 would build, in the same column
+ * order: [intercept] numeric columns, then for c = 0..n_cat-1 the n_levels[c] level columns of categorical c
+ * (dlsa/models.py:71-79).  Level-by-numeric blocks run on DMMA with a one-hot operand (level tiles untouched by a
+ * 4-row step are skipped), level-by-level counts and the level gradient are 64-bit fixed-point sums (order-independent).
+ *
+ *   numeric  [n, ldn] float64, n_num <= 7 columns used; mean/std [n_num] or both NULL: x <- (x-mean)/std (:99-101)
+ *   codes    [n, n_cat] int32, codes[i,c] in [0, n_levels[c]) or -1 for the baseline level (no column)
+ *   n_levels_host [n_cat] HOST ints (1 <= n_cat <= 8, sum <= 192)
+ *   p = fit_intercept + n_num + sum(n_levels);  beta/g [K,p], H [K,p,p], loglik [K] or NULL; active as in K1.
+ * DLSA_E_UNSUPPORTED when the shape limits above are exceeded (expand and use dlsa_irls_pass_f64 instead).
+ */
+size_t dlsa_irls_pass_cat_workspace_bytes(int K, int n_cat, const int *n_levels_host, int64_t max_part_rows);
+int dlsa_irls_pass_cat_f64(const double *numeric, int64_t ldn, int n_num, const double *mean, const double *std,
+                           const int *codes, int n_cat, const int *n_levels_host, const double *y,
+                           const int64_t *part_off, int K, int fit_intercept, const double *beta, const int *active,
+                           double *g, double *H, double *loglik, int64_t max_part_rows, void *workspace,
+                           size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K2  batched p x p Cholesky solve + Newton update for every active partition.
  * Replaces  del = solve(hess)%*%grad; damping; beta = beta + del; stop rule   dlsa/R/wlse_func.R:55-62
  *           (and sklearn's inner CG + line search, dlsa/models.py:110-113).

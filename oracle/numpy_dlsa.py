@@ -107,6 +107,36 @@ def logistic_fit(X, y, fit_intercept=False, tol=1e-10, max_iter=50):
 
 
 # --------------------------------------------------------------------------------------------
+# a2 dummy branch on the compact representation                       dlsa/models.py:56-79,99-101
+# --------------------------------------------------------------------------------------------
+
+
+def expand_onehot(numeric, codes, n_levels, mean=None, std=None):
+    """The dense design the dummy branch of logistic_model builds (dlsa/models.py:56-79): numeric columns first
+    (optionally standardised ``(x-mean)/std``, :99-101), then for every categorical column c its ``n_levels[c]`` 0/1
+    level columns (``pd.get_dummies``, :62-65, after the baseline level was dropped, :78).  ``codes[i, c]`` is the
+    index of row i's level inside column c's block, or -1 for the baseline level (all zeros)."""
+    numeric = np.zeros((codes.shape[0], 0)) if numeric is None else np.asarray(numeric, dtype=np.float64)
+    n = codes.shape[0]
+    num = numeric if mean is None else (numeric - np.asarray(mean)) / np.asarray(std)
+    blocks = [num]
+    for c, L in enumerate(n_levels):
+        B = np.zeros((n, L))
+        rows = np.nonzero(codes[:, c] >= 0)[0]
+        B[rows, codes[rows, c]] = 1.0
+        blocks.append(B)
+    return np.concatenate(blocks, axis=1)
+
+
+def irls_pass_cat(numeric, codes, n_levels, y, beta, fit_intercept=False, mean=None, std=None):
+    """What kernel K1c must produce for one partition: ``irls_pass`` on the expanded design (intercept first)."""
+    X = expand_onehot(numeric, codes, n_levels, mean, std)
+    if fit_intercept:
+        X = np.concatenate([np.ones((X.shape[0], 1)), X], axis=1)
+    return irls_pass(X, y, beta)
+
+
+# --------------------------------------------------------------------------------------------
 # a10  linear / OLS block                                             dlsa/R/wlse_func.R:169-182
 # --------------------------------------------------------------------------------------------
 

@@ -1,0 +1,156 @@
+"""GPU parity of the compact categorical pass K1c (dlsa_irls_pass_cat_f64) — the dummy branch of logistic_model
+(dlsa/models.py:56-91) computed without materialising the one-hot columns — against the oracle and against the dense
+CUDA pass on the expanded matrix."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_dlsa as onp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dlsa_b200 import engine
+    return engine
+
+
+def dev(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
+
+
+def relfro(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def make_case(rng, sizes, n_num, n_levels, baseline_share=0.15, zipf=True):
+    off = np.zeros(len(sizes) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(sizes)
+    n = int(off[-1])
+    numeric = rng.standard_normal((n, n_num))
+    codes = np.empty((n, len(n_levels)), dtype=np.int32)
+    for c, L in enumerate(n_levels):
+        w = 1.0 / np.arange(1, L + 1) if zipf else np.ones(L)
+        lv = rng.choice(L, size=n, p=w / w.sum())
+        lv[rng.random(n) < baseline_share] = -1
+        codes[:, c] = lv
+    y = (rng.random(n) < 0.4).astype(np.float64)
+    return off, numeric, codes, y
+
+
+CASES = [
+    # (n_num, n_levels, intercept, standardise)
+    (7, [11, 6, 7, 75, 75], True, False),     # the airline shape: p = 182
+    (7, [11, 6, 7, 75, 75], False, True),
+    (2, [3, 4], True, False),                 # the dummy-layout KAT shape class
+    (0, [5], False, False),                   # pure categorical, one column
+    (0, [9, 17, 2], True, False),
+    (3, [8, 8, 8, 8, 8, 8, 8, 8], True, True),  # 8 categorical columns, tiles aligned with the blocks
+    (5, [1, 1, 30, 100], False, False),       # 132 levels -> 17 tiles
+    (6, [40, 60, 90], True, False),           # 190 levels -> 24 tiles
+]
+
+
+@pytest.mark.parametrize("n_num,n_levels,icpt,standardise", CASES)
+def test_cat_pass_matches_oracle(eng, n_num, n_levels, icpt, standardise):
+    rng = np.random.default_rng(n_num * 31 + len(n_levels) * 7 + icpt)
+    sizes = [0, 1, 31, 32, 33, 257, 1000, 4097, 64, 5]
+    off, numeric, codes, y = make_case(rng, sizes, n_num, n_levels)
+    p = int(icpt) + n_num + sum(n_levels)
+    beta = rng.standard_normal((len(sizes), p)) * 0.4
+    mean = std = None
+    if standardise:
+        mean, std = rng.standard_normal(n_num) * 0.3, 0.5 + rng.random(n_num)
+    g, H, ll = eng.irls_pass_cat(dev(numeric) if n_num else None, dev(codes, torch.int32), n_levels, dev(y),
+                                 dev(off, torch.int64), dev(beta), fit_intercept=icpt,
+                                 mean=None if mean is None else dev(mean), std=None if std is None else dev(std))
+    g, H, ll = g.cpu().numpy(), H.cpu().numpy(), ll.cpu().numpy()
+    for k, nk in enumerate(sizes):
+        sl = slice(off[k], off[k + 1])
+        g0, H0, ll0 = onp.irls_pass_cat(numeric[sl], codes[sl], n_levels, y[sl], beta[k], icpt, mean, std)
+        assert np.allclose(g[k], g0, rtol=1e-10, atol=1e-9), (k, nk, np.abs(g[k] - g0).max())
+        assert np.allclose(H[k], H0, rtol=1e-10, atol=1e-10), (k, nk, np.abs(H[k] - H0).max())
+        assert abs(ll[k] - ll0) <= 1e-11 * max(1.0, abs(ll0))
+        assert np.array_equal(H[k], H[k].T)
+
+
+def test_cat_pass_equals_dense_cuda_pass_on_expanded_matrix(eng):
+    """K1c against K1 (tiled dense kernel) fed with dlsa_onehot_expand_f64's matrix: big sliced partitions, skipped
+    (inactive) partitions left untouched, bitwise run-to-run reproducibility."""
+    from dlsa_b200._lib import lib, check
+    rng = np.random.default_rng(3)
+    n_levels = [11, 6, 7, 75, 75]
+    sizes = [150_000, 90_001, 40_000]
+    off, numeric, codes, y = make_case(rng, sizes, 7, n_levels, baseline_share=0.1)
+    n, K = int(off[-1]), len(sizes)
+    px = 7 + sum(n_levels)
+    p = px + 1
+    beta = rng.standard_normal((K, p)) * 0.3
+    num_d, codes_d, y_d, off_d, beta_d = dev(numeric), dev(codes, torch.int32), dev(y), dev(off, torch.int64), dev(beta)
+    X = torch.zeros(n, px, dtype=torch.float64, device="cuda")
+    base = np.concatenate([[7], 7 + np.cumsum(n_levels)[:-1]]).astype(np.int32)
+    check(lib.dlsa_onehot_expand_f64(num_d.data_ptr(), 7, None, None, codes_d.data_ptr(), len(n_levels),
+                                     dev(base, torch.int32).data_ptr(), n, X.data_ptr(), X.stride(0),
+                                     torch.cuda.current_stream().cuda_stream), "onehot")
+    g0, H0, ll0 = eng.irls_pass(X, y_d, off_d, beta_d, fit_intercept=True)
+    active = torch.tensor([1, 0, 1], dtype=torch.int32, device="cuda")
+    out = (torch.full((K, p), 7.0, dtype=torch.float64, device="cuda"),
+           torch.full((K, p, p), 7.0, dtype=torch.float64, device="cuda"),
+           torch.full((K,), 7.0, dtype=torch.float64, device="cuda"))
+    g1, H1, ll1 = eng.irls_pass_cat(num_d, codes_d, n_levels, y_d, off_d, beta_d, fit_intercept=True, active=active, out=out)
+    for k in (0, 2):
+        assert relfro(H1[k].cpu().numpy(), H0[k].cpu().numpy()) < 1e-12
+        assert np.allclose(g1[k].cpu().numpy(), g0[k].cpu().numpy(), rtol=1e-10, atol=1e-8)
+        assert abs(float(ll1[k] - ll0[k])) < 1e-9 * abs(float(ll0[k]))
+    assert torch.all(H1[1] == 7.0) and torch.all(g1[1] == 7.0) and float(ll1[1]) == 7.0
+    g2, H2, ll2 = eng.irls_pass_cat(num_d, codes_d, n_levels, y_d, off_d, beta_d, fit_intercept=True)
+    g3, H3, ll3 = eng.irls_pass_cat(num_d, codes_d, n_levels, y_d, off_d, beta_d, fit_intercept=True)
+    assert torch.equal(H2, H3) and torch.equal(g2, g3) and torch.equal(ll2, ll3)
+    assert torch.equal(H2[0], H1[0])
+
+
+def test_cat_fit_matches_oracle_fit_and_selection(eng):
+    """Whole map -> combine -> LARS on the compact airline-shaped design vs the oracle run on the expanded matrix."""
+    from dlsa_b200 import synth
+    n, K = 60_000, 4
+    numeric, codes, n_levels, y = synth.airline_shaped_device(n, 5, torch.device("cuda"))
+    # keep the level space small enough that every level is populated in every partition
+    n_levels = [11, 6, 7, 9, 9]
+    codes = codes.clone()
+    for c, L in enumerate(n_levels):
+        codes[:, c] = torch.where(codes[:, c] >= L, torch.full_like(codes[:, c], -1), codes[:, c])
+    off = synth.equal_partition_offsets(n, K, torch.device("cuda"))
+    fits = eng.fit_logistic_partitions_cat(numeric, codes, n_levels, y, off, fit_intercept=True)
+    assert int(fits.status.abs().sum()) == 0
+    comb = eng.combine_partitions(fits)
+    path = eng.lars_path(comb.Sig_inv_sum, comb.beta_byOLS, True, float(n))
+    Xh = onp.expand_onehot(numeric.cpu().numpy(), codes.cpu().numpy(), n_levels)
+    yh, offh = y.cpu().numpy(), off.cpu().numpy()
+    coefs, sigs = zip(*[onp.logistic_fit(Xh[offh[k]:offh[k + 1]], yh[offh[k]:offh[k + 1]], fit_intercept=True)[:2]
+                        for k in range(K)])
+    for k in range(K):
+        assert np.max(np.abs(fits.coef[k].cpu().numpy() - coefs[k])) < 1e-8
+        assert relfro(fits.Sig_inv[k].cpu().numpy(), sigs[k]) < 1e-9
+    theta, oneshot, S = onp.combine(np.stack(coefs), np.stack(sigs))
+    assert np.max(np.abs(comb.beta_byOLS.cpu().numpy() - theta)) < 1e-6
+    assert relfro(comb.Sig_inv_sum.cpu().numpy(), S) < 1e-9
+    ref = onp.lars_lsa(S, theta, True, float(n))
+    assert path.argmin_BIC == int(np.argmin(ref["BIC"])) and path.argmin_AIC == int(np.argmin(ref["AIC"]))
+    assert np.array_equal(path.beta[path.argmin_BIC].cpu().numpy() != 0, ref["beta"][path.argmin_BIC] != 0)
+
+
+def test_cat_pass_rejects_unsupported_shapes(eng):
+    from dlsa_b200._lib import DlsaLibraryError
+    n = 64
+    codes = torch.zeros(n, 1, dtype=torch.int32, device="cuda")
+    y = torch.zeros(n, dtype=torch.float64, device="cuda")
+    off = torch.tensor([0, n], dtype=torch.int64, device="cuda")
+    with pytest.raises(DlsaLibraryError):  # 8 numerics: z = [1 | numerics] no longer fits one tile
+        eng.irls_pass_cat(torch.zeros(n, 8, dtype=torch.float64, device="cuda"), codes, [3], y, off,
+                          torch.zeros(1, 11, dtype=torch.float64, device="cuda"))
+    with pytest.raises(DlsaLibraryError):  # 200 levels
+        eng.irls_pass_cat(None, codes, [200], y, off, torch.zeros(1, 200, dtype=torch.float64, device="cuda"))
+    assert not eng.cat_supported(8, [3]) and not eng.cat_supported(2, [100, 100]) and eng.cat_supported(7, [11, 6, 7, 75, 75])

@@ -37,6 +37,53 @@ CASES = {
 }
 
 
+# compact categorical pass K1c on the airline-shaped design (7 numerics + 5 categorical columns, p = 182): name -> (rows, K)
+CAT_CASES = {
+    "c3_cat": (15_000_000, 15),        # one GPU's shard of C3 at G=8 — compare with the dense "c3" line
+    "c3_cat_full": (120_000_000, 120), # the WHOLE C3 data set on one GPU (10 GB compact instead of 174 GB dense)
+    "c3_cat_k1024": (60_000_000, 1024),
+}
+
+
+def run_cat(name, reps, hbm):
+    from dlsa_b200 import synth as sy
+    n, K = CAT_CASES[name]
+    dev = torch.device("cuda", 0)
+    numeric, codes, n_levels, y = sy.airline_shaped_device(n, 7, dev)
+    off = sy.equal_partition_offsets(n, K, dev)
+    p = 1 + numeric.shape[1] + sum(n_levels)
+    beta = 0.05 * torch.randn(K, p, dtype=torch.float64, device=dev)
+    max_rows = int((off[1:] - off[:-1]).max().item())
+    g = torch.zeros(K, p, dtype=torch.float64, device=dev)
+    H = torch.zeros(K, p, p, dtype=torch.float64, device=dev)
+    import ctypes as C
+    nl = (C.c_int * len(n_levels))(*n_levels)
+    ws = engine._workspace(_lib.lib.dlsa_irls_pass_cat_workspace_bytes(K, len(n_levels), nl, max_rows), dev)
+
+    def run():
+        engine.irls_pass_cat(numeric, codes, n_levels, y, off, beta, True, None, None, None, max_rows,
+                             want_loglik=False, out=(g, H, None), workspace=ws)
+
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sorted(times)[len(times) // 2]
+    bytes_row = 8 * numeric.shape[1] + 4 * codes.shape[1] + 8
+    gbs = n * bytes_row / (ms * 1e-3) / 1e9
+    return {"case": name, "kernel": "irls_cat_kernel (K1c)", "rows": n, "p": p, "K": K, "family": "logistic",
+            "ms_per_pass": round(ms, 4), "ms_min": round(min(times), 4), "rows_per_s_per_pass": n / (ms * 1e-3),
+            "algorithmic_bytes_per_row": bytes_row, "GBps": round(gbs, 1), "hbm_frac": round(gbs / hbm, 4),
+            "dense_equivalent_bytes_per_row": 8 * p, "finite": bool(torch.isfinite(H).all().item())}
+
+
 def peaks():
     hbm = 6550.0
     try:
@@ -64,6 +111,12 @@ def main():
     hbm, f64 = peaks()
     lines = []
     for name in args.cases.split(","):
+        if name in CAT_CASES:
+            line = run_cat(name, args.reps, hbm)
+            print(json.dumps(line), flush=True)
+            lines.append(line)
+            torch.cuda.empty_cache()
+            continue
         n, px, K, icpt, fam, law = CASES[name]
         p = px + int(icpt)
         ldx = px + (px & 1)  # odd px is stored with an even row pitch (16-byte aligned rows -> TMA row copies)
