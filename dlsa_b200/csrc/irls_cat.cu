@@ -6,15 +6,20 @@
 //   g = X'(y - prob),  H = X' diag(prob(1-prob)) X,  loglik.
 // A row of the expanded X is z = [1 | x_1..x_q] (q <= 7 numerics) plus ONE 1 per categorical column, so
 //   H[z, z]           = sum w z z'                         one DMMA per 4 rows (8x8 tile)
-//   H[level, z]       = sum_{rows at that level} w z'      DMMA with a one-hot A operand built in registers; tiles of 8
-//                                                          levels that none of the 4 rows touches are skipped
+//   H[level, z]       = sum_{rows at that level} w z'      scatter-add into a WARP-PRIVATE shared-memory table
+//   g[level]          = sum_{rows at that level} r          [level][9]: 8 lanes per (row, categorical) + 1 for g, rows
+//                                                          taken two at a time with in-register forwarding when both
+//                                                          hit the same level — no atomics, fixed summation order
 //   H[level, level]   = H[level, 1]  (the intercept column of the block above)
 //   H[level, level']  = sum w over rows holding both       (different categorical columns) — a weighted 2-D histogram:
 //                                                          64-bit fixed-point RED.ADD into an L2-resident table
-//   g[level]          = sum r over rows at that level      same, fixed-point
-// Algorithmic traffic per row: 8 q + 4 c + 8 bytes (airline shape: 84 B instead of 1456 B), flops ~ 2*(64 + 64 c) instead of
-// p^2 + 5p.  Fixed-point sums are exact integer additions => the histogram part is bitwise independent of the order
-// in which rows arrive; resolution 2^-44 (w <= 1/4) and 2^-42 (|r| < 1) against sums of at most 2^20 rows per CTA.
+// Algorithmic traffic per row: 8 q + 4 c + 8 bytes (airline shape: 84 B instead of 1456 B).  Fixed-point sums are
+// exact integer additions => the histogram part is bitwise independent of the order in which rows arrive; resolution
+// 2^-44 (w <= 1/4) against sums of at most 2^20 rows per CTA.
+//
+// v1 of this kernel did H[level, z] on DMMA with a one-hot operand and per-tile skipping (profiles/r01_k1c_*_v1.*):
+// ptxas predicates the skipped DMMAs and a predicated-off DMMA still holds the FP64 pipe for 16 cycles, so all 25
+// tile slots per 4 rows were paid (3.07 ms for 15M rows); an indirect-branch dispatch was slower still (5.0 ms).
 #include "common.cuh"
 
 namespace dlsa {
@@ -23,17 +28,18 @@ namespace {
 
 constexpr int kCatMaxC = 8;      // categorical columns
 constexpr int kCatMaxNum = 7;    // numeric columns (z = [1 | numerics] fills one 8-wide tile)
-constexpr int kCatWarps = 8;
-constexpr int kCatStages = 4;
-constexpr int kCatThreads = kCatWarps * 32;
+constexpr int kCatMaxWarps = 12;
+constexpr int kCatStages = 3;
 constexpr int kCatMaxRowsPerCta = 1 << 20;
-constexpr double kWScale = 17592186044416.0;      // 2^44
-constexpr double kRScale = 4398046511104.0;       // 2^42
+constexpr int kCatMaxLevels = 248;  // one byte per level index, 0xFF = no level
+constexpr int kTabPitch = 9;        // doubles per level: w*z (8) | r
+constexpr double kWScale = 17592186044416.0;  // 2^44
 // per-warp, per-stage shared memory: 32 rows of numerics (7 doubles), codes (8 ints), labels
 constexpr int kStageZ = 32 * kCatMaxNum * 8;
 constexpr int kStageC = 32 * kCatMaxC * 4;
 constexpr int kStageY = 32 * 8;
 constexpr int kStageBytes = kStageZ + kStageC + kStageY;  // 3072
+constexpr int kRowScratch = 32 * 16 + 32 * 8;              // (w, r) per row | packed level bytes per row
 
 struct CatArgs {
     const double* num;
@@ -49,13 +55,12 @@ struct CatArgs {
     int fit_intercept, want_ll;
     const double* beta;
     const int* active;
-    int Ltot, npairs;
+    int Ltot, Lpad, npairs;
     int cat_lo[kCatMaxC + 1];            // level-space offsets of each categorical column
     int pair_off[kCatMaxC * kCatMaxC];   // offset of the (c, c') block, c < c', in the pair table
-    double* part_d;                      // [K*S, stride_d]: Dz 64 | gz 8 | ll 1 | pad | B [NT*64]
-    unsigned long long* part_i;          // [K*S, stride_i]: gl [Lpad] | pairs [npairs]
+    double* part_d;                      // [K*S, stride_d]: Dz 64 | gz 8 | ll 1 | pad to 80 | table [Lpad][9]
+    unsigned long long* part_i;          // [K*S, stride_i]: pairs [npairs]
     int64_t stride_d, stride_i;
-    int Lpad;
 };
 
 __device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, bool pred) {
@@ -75,33 +80,41 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, long long v) 
     asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// NT = 8-level tiles of the concatenated level space held in registers, NC = categorical columns compiled in.
-template <int NT, int NC>
-__global__ void __launch_bounds__(kCatThreads, 1) irls_cat_kernel(const CatArgs a) {
+// ROUNDS = ceil(9 * n_cat / 32): scatter slots (categorical c, column j in 0..8) are dealt to the 32 lanes round by round.
+// NC = categorical columns compiled into the row stage (4 or 8).
+template <int ROUNDS, int NC>
+__global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const CatArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = blockIdx.x / a.S;
     const int s = blockIdx.x - k * a.S;
     if (a.active != nullptr && a.active[k] == 0) return;
+    const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_num = a.n_num, n_cat = a.n_cat;
+    const int tab_doubles = a.Lpad * kTabPitch;
 
-    // shared: [warps][stages] rings | beta (8 + Lpad) | reduction buffer (NT*64 + 80)
-    unsigned char* ring = smem_raw + (size_t)warp * kCatStages * kStageBytes;
-    double* bz = reinterpret_cast<double*>(smem_raw + (size_t)kCatWarps * kCatStages * kStageBytes);
+    // shared: per warp [ring | row scratch | table] ; then beta (8 + Lpad)
+    const size_t per_warp = (size_t)kCatStages * kStageBytes + kRowScratch + (size_t)tab_doubles * 8;
+    unsigned char* mine = smem_raw + (size_t)warp * per_warp;
+    unsigned char* ring = mine;
+    double* wr = reinterpret_cast<double*>(mine + kCatStages * kStageBytes);                       // [32][2]
+    unsigned long long* lv = reinterpret_cast<unsigned long long*>(mine + kCatStages * kStageBytes + 512);  // [32]
+    double* tab = reinterpret_cast<double*>(mine + kCatStages * kStageBytes + kRowScratch);
+    double* bz = reinterpret_cast<double*>(smem_raw + (size_t)nwarps * per_warp);
     double* bl = bz + 8;
-    double* red = bl + a.Lpad;
 
-    // coefficients in internal order: [intercept | numerics (7) | levels]
+    // coefficients in internal order: [intercept | numerics (7) | levels]; zero this warp's table
     {
         const int p = a.fit_intercept + n_num + a.Ltot;
         const double* bk = a.beta + (size_t)k * p;
-        for (int i = threadIdx.x; i < 8 + a.Lpad; i += kCatThreads) {
+        for (int i = threadIdx.x; i < 8 + a.Lpad; i += blockDim.x) {
             double v = 0.0;
             if (i == 0) v = a.fit_intercept ? bk[0] : 0.0;
             else if (i < 8) v = (i - 1 < n_num) ? bk[a.fit_intercept + i - 1] : 0.0;
             else if (i - 8 < a.Ltot) v = bk[a.fit_intercept + n_num + (i - 8)];
             bz[i] = v;
         }
+        for (int i = lane; i < tab_doubles; i += 32) tab[i] = 0.0;
     }
     __syncthreads();
 
@@ -112,14 +125,13 @@ __global__ void __launch_bounds__(kCatThreads, 1) irls_cat_kernel(const CatArgs 
     const int64_t r0 = p0 + (int64_t)s * per;
     const int64_t r1 = (r0 + per < p1) ? r0 + per : p1;
     const int64_t ngroups = r1 > r0 ? (r1 - r0 + 31) / 32 : 0;
-    const int64_t my_groups = ngroups > warp ? (ngroups - warp + kCatWarps - 1) / kCatWarps : 0;
+    const int64_t my_groups = ngroups > warp ? (ngroups - warp + nwarps - 1) / nwarps : 0;
 
-    unsigned long long* gl = a.part_i + (size_t)blockIdx.x * a.stride_i;
-    unsigned long long* pairs = gl + a.Lpad;
+    unsigned long long* pairs = a.part_i + (size_t)blockIdx.x * a.stride_i;
 
     auto issue = [&](int64_t gi) {  // cp.async the gi-th group of this warp into stage gi % kCatStages
         if (gi < my_groups) {
-            const int64_t R0 = r0 + (warp + gi * kCatWarps) * 32;
+            const int64_t R0 = r0 + (warp + gi * nwarps) * 32;
             const int nv = (int)((r1 - R0 < 32) ? (r1 - R0) : 32);
             unsigned char* st = ring + (size_t)(gi % kCatStages) * kStageBytes;
             const uint32_t zs = smem_u32(st), cs = zs + kStageZ, ys = cs + kStageC;
@@ -149,9 +161,21 @@ __global__ void __launch_bounds__(kCatThreads, 1) irls_cat_kernel(const CatArgs 
         cp_async_commit();  // one (possibly empty) group per call keeps the wait_group arithmetic uniform
     };
 
-    double acc[2 * NT];
+    // per-lane scatter slots: round q handles slot 32 q + lane = (categorical c, column j); j = 8 is the g column
+    int slot_sh[ROUNDS];    // bit shift of categorical c's byte in the packed level word, or -1 (idle lane)
+    int slot_j[ROUNDS];     // table column 0..8
+    int slot_z[ROUNDS];     // offset of the z value inside a numerics row, -1 => 1.0 (intercept / g), -2 => 0.0
 #pragma unroll
-    for (int i = 0; i < 2 * NT; ++i) acc[i] = 0.0;
+    for (int q = 0; q < ROUNDS; ++q) {
+        const int sidx = 32 * q + lane;
+        int c = -1, j = 0;
+        if (sidx < 8 * n_cat) { c = sidx >> 3; j = sidx & 7; }
+        else if (sidx < 9 * n_cat) { c = sidx - 8 * n_cat; j = 8; }
+        slot_sh[q] = c < 0 ? -1 : 8 * c;
+        slot_j[q] = j;
+        slot_z[q] = (j == 0 || j == 8) ? -1 : (j - 1 < n_num ? j - 1 : -2);
+    }
+
     double dz0 = 0.0, dz1 = 0.0, ll = 0.0;
     double gz[8];
 #pragma unroll
@@ -159,12 +183,12 @@ __global__ void __launch_bounds__(kCatThreads, 1) irls_cat_kernel(const CatArgs 
 
     for (int64_t gi = 0; gi < kCatStages - 1; ++gi) issue(gi);
 
-    const int jcol = lane >> 2;  // the z column / level-within-tile this lane holds in the MMA fragments
+    const int jcol = lane >> 2;  // the z column this lane holds in the MMA fragments
     for (int64_t gi = 0; gi < my_groups; ++gi) {
         issue(gi + kCatStages - 1);
         cp_async_wait<kCatStages - 1>();
         __syncwarp();
-        const int64_t R0 = r0 + (warp + gi * kCatWarps) * 32;
+        const int64_t R0 = r0 + (warp + gi * nwarps) * 32;
         const int nv = (int)((r1 - R0 < 32) ? (r1 - R0) : 32);
         unsigned char* st = ring + (size_t)(gi % kCatStages) * kStageBytes;
         double* zs = reinterpret_cast<double*>(st);
@@ -189,7 +213,7 @@ __global__ void __launch_bounds__(kCatThreads, 1) irls_cat_kernel(const CatArgs 
             }
         }
         int lev[NC];
-        uint32_t plo = 0xFFFFFFFFu, phi = 0xFFFFFFFFu;
+        unsigned long long packed = ~0ull;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             lev[c] = -1;
@@ -200,9 +224,7 @@ __global__ void __launch_bounds__(kCatThreads, 1) irls_cat_kernel(const CatArgs 
                     eta += bl[lev[c]];
                 }
             }
-            const uint32_t byte = (uint32_t)(lev[c] & 0xFF);
-            if (c < 4) plo = (plo & ~(0xFFu << (8 * c))) | (byte << (8 * c));
-            else phi = (phi & ~(0xFFu << (8 * (c - 4)))) | (byte << (8 * (c - 4)));
+            packed = (packed & ~(0xFFull << (8 * c))) | ((unsigned long long)(lev[c] & 0xFF) << (8 * c));
         }
         double w = 0.0, r = 0.0;
         if (valid) {
@@ -215,13 +237,13 @@ __global__ void __launch_bounds__(kCatThreads, 1) irls_cat_kernel(const CatArgs 
         gz[0] += r;
 #pragma unroll
         for (int j = 0; j < kCatMaxNum; ++j) gz[1 + j] = fma(r, z[j], gz[1 + j]);
+        *reinterpret_cast<double2*>(wr + 2 * lane) = make_double2(w, r);
+        lv[lane] = packed;
         {
             const long long wfix = __double2ll_rn(w * kWScale);
-            const long long rfix = __double2ll_rn(r * kRScale);
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 if (lev[c] >= 0) {
-                    red_add_u64(gl + lev[c], rfix);
 #pragma unroll
                     for (int d = c + 1; d < NC; ++d)
                         if (lev[d] >= 0)
@@ -232,40 +254,54 @@ __global__ void __launch_bounds__(kCatThreads, 1) irls_cat_kernel(const CatArgs 
                 }
             }
         }
-        if (a.mean != nullptr) __syncwarp();
+        __syncwarp();
 
-        // ---- MMA stage: 8 k-steps of 4 rows ------------------------------------------------------------------
-#pragma unroll 2
+        // ---- dense z block: 8 k-steps of 4 rows, one DMMA each ------------------------------------------------------
+#pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
             const int src = 4 * ks + (lane & 3);
-            const double wk = __shfl_sync(0xffffffffu, w, src);
-            const uint32_t qlo = __shfl_sync(0xffffffffu, plo, src);
-            uint32_t qhi = 0xFFFFFFFFu;
-            if (NC > 4) qhi = __shfl_sync(0xffffffffu, phi, src);
             double zz = 1.0;
             if (jcol > 0) zz = (jcol - 1 < n_num) ? zs[src * n_num + jcol - 1] : 0.0;
-            const double b = wk * zz;
-            dmma884(dz0, dz1, zz, b);
-            uint32_t mine = 0;
+            dmma884(dz0, dz1, zz, wr[2 * src] * zz);
+        }
+
+        // ---- level blocks: scatter-add into the warp's table, two rows per step ------------------------------------
+        // Lane (c, j) always owns column j of categorical c's levels, so successive rows that hit the same level are
+        // ordered by program order of ONE thread; inside a row pair the second row's sum is forwarded in registers.
+#pragma unroll 4
+        for (int rp = 0; rp < 16; ++rp) {
+            const int ra = 2 * rp, rb = ra + 1;
+            const unsigned long long pa = lv[ra], pb = lv[rb];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const uint32_t lv = ((c < 4 ? qlo : qhi) >> (8 * (c & 3))) & 0xFFu;
-                if ((int)(lv & 7u) == jcol) mine |= 1u << (lv >> 3);  // lv = 0xFF (no level) sets bit 31: never a tile
-            }
-            const uint32_t hit = __reduce_or_sync(0xffffffffu, mine);
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                if ((hit >> t) & 1u) {
-                    const double av = __hiloint2double((int)(((mine >> t) & 1u) * 0x3FF00000u), 0);
-                    dmma884(acc[2 * t], acc[2 * t + 1], av, b);
+            for (int q = 0; q < ROUNDS; ++q) {
+                if (slot_sh[q] >= 0) {
+                    const uint32_t la = (uint32_t)(pa >> slot_sh[q]) & 0xFFu;
+                    const uint32_t lb = (uint32_t)(pb >> slot_sh[q]) & 0xFFu;
+                    const int sel = slot_j[q] == 8 ? 1 : 0;
+                    double va = wr[2 * ra + sel], vb = wr[2 * rb + sel];
+                    if (slot_z[q] >= 0) {
+                        va *= zs[ra * n_num + slot_z[q]];
+                        vb *= zs[rb * n_num + slot_z[q]];
+                    } else if (slot_z[q] == -2) {
+                        va = 0.0;
+                        vb = 0.0;
+                    }
+                    const bool oka = la != 0xFFu, okb = lb != 0xFFu;
+                    double* qa = tab + (oka ? la : 0u) * kTabPitch + slot_j[q];
+                    double* qb = tab + (okb ? lb : 0u) * kTabPitch + slot_j[q];
+                    const double ta = *qa, tb = *qb;
+                    const double na = ta + va;
+                    const double nb = ((oka && la == lb) ? na : tb) + vb;
+                    if (oka) *qa = na;
+                    if (okb) *qb = nb;
                 }
             }
         }
-        __syncwarp();  // the stage is re-filled by the next issue()
+        __syncwarp();  // the stage and the row scratch are re-filled by the next iteration
     }
     cp_async_wait<0>();
 
-    // ---- CTA reduction in a fixed warp order, then the partial goes to the workspace ---------------------------
+    // ---- CTA reduction in a fixed warp order, straight into the workspace partial ----------------------------------
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -273,31 +309,33 @@ __global__ void __launch_bounds__(kCatThreads, 1) irls_cat_kernel(const CatArgs 
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) ll += shfl_xor_f64(ll, m);
-    const int di = lane >> 2, dj = 2 * (lane & 3);
-    for (int wv = 0; wv < kCatWarps; ++wv) {
-        if (warp == wv) {
-            const bool first = wv == 0;
-            // red: Dz [64] | gz [8] | ll | pad to 80 | B tiles [NT][8][8]
-            red[di * 8 + dj] = (first ? 0.0 : red[di * 8 + dj]) + dz0;
-            red[di * 8 + dj + 1] = (first ? 0.0 : red[di * 8 + dj + 1]) + dz1;
-            if (lane < 8) {
-                double v = gz[0];
+    __syncthreads();  // every warp is done with its ring: reuse stage 0 of each ring for the small per-warp results
+    {
+        double* sm = reinterpret_cast<double*>(ring);  // Dz 64 | gz 8 | ll
+        const int di = lane >> 2, dj = 2 * (lane & 3);
+        sm[di * 8 + dj] = dz0;
+        sm[di * 8 + dj + 1] = dz1;
+        if (lane < 8) {
+            double v = gz[0];
 #pragma unroll
-                for (int j = 1; j < 8; ++j) v = (lane == j) ? gz[j] : v;
-                red[64 + lane] = (first ? 0.0 : red[64 + lane]) + v;
-            }
-            if (lane == 8) red[72] = (first ? 0.0 : red[72]) + ll;
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                double* o = red + 80 + t * 64 + di * 8 + dj;
-                o[0] = (first ? 0.0 : o[0]) + acc[2 * t];
-                o[1] = (first ? 0.0 : o[1]) + acc[2 * t + 1];
-            }
+            for (int j = 1; j < 8; ++j) v = (lane == j) ? gz[j] : v;
+            sm[64 + lane] = v;
         }
-        __syncthreads();
+        if (lane == 8) sm[72] = ll;
     }
+    __syncthreads();
     double* out = a.part_d + (size_t)blockIdx.x * a.stride_d;
-    for (int i = threadIdx.x; i < 80 + NT * 64; i += kCatThreads) out[i] = red[i];
+    for (int i = threadIdx.x; i < 80 + tab_doubles; i += blockDim.x) {
+        double v = 0.0;
+        if (i < 73) {
+            for (int wv = 0; wv < nwarps; ++wv) v += reinterpret_cast<const double*>(smem_raw + (size_t)wv * per_warp)[i];
+        } else if (i >= 80) {
+            for (int wv = 0; wv < nwarps; ++wv)
+                v += reinterpret_cast<const double*>(smem_raw + (size_t)wv * per_warp + kCatStages * kStageBytes +
+                                                     kRowScratch)[i - 80];
+        }
+        out[i] = v;
+    }
 }
 
 // Assemble the full symmetric H [p, p], g [p] and loglik of every active partition from its S partials, slices summed in a
@@ -332,18 +370,18 @@ __global__ void irls_cat_finalize_kernel(const CatArgs a, double* __restrict__ g
         if (u2 < 8) {
             for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + u1 * 8 + u2];
         } else if (u1 < 8) {
-            for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + 80 + (u2 - 8) * 8 + u1];
+            for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + 80 + (u2 - 8) * kTabPitch + u1];
         } else {
             const int l1 = u1 - 8, l2 = u2 - 8;
             if (l1 == l2) {
-                for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + 80 + l1 * 8];
+                for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + 80 + l1 * kTabPitch];
             } else {
                 const int c1 = cat_of(l1), c2 = cat_of(l2);
                 if (c1 != c2) {
                     const int idx = a.pair_off[c1 * kCatMaxC + c2] + (l1 - a.cat_lo[c1]) * (a.cat_lo[c2 + 1] - a.cat_lo[c2]) +
                                     (l2 - a.cat_lo[c2]);
                     for (int sl = 0; sl < a.S; ++sl)  // per-slice conversion: a slice sum is < 2^63, the partition sum may not be
-                        v += (double)(long long)pi[sl * a.stride_i + a.Lpad + idx] * (1.0 / kWScale);
+                        v += (double)(long long)pi[sl * a.stride_i + idx] * (1.0 / kWScale);
                 }
             }
         }
@@ -356,7 +394,7 @@ __global__ void irls_cat_finalize_kernel(const CatArgs a, double* __restrict__ g
         if (u < 8) {
             for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + 64 + u];
         } else {
-            for (int sl = 0; sl < a.S; ++sl) v += (double)(long long)pi[sl * a.stride_i + (u - 8)] * (1.0 / kRScale);
+            for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + 80 + (u - 8) * kTabPitch + 8];
         }
         g[(size_t)k * p + o] = v;
     }
@@ -368,9 +406,9 @@ __global__ void irls_cat_finalize_kernel(const CatArgs a, double* __restrict__ g
 }
 
 struct CatPlan {
-    int Ltot, Lpad, NT, NTb, npairs, S;
+    int Ltot, Lpad, npairs, S, warps;
     int64_t stride_d, stride_i;
-    size_t bytes_d, bytes_i;
+    size_t bytes_d, bytes_i, smem;
 };
 
 int cat_sm_count() {
@@ -384,29 +422,34 @@ int cat_sm_count() {
     return sms;
 }
 
-bool cat_plan(int K, int n_cat, const int* n_levels, int64_t max_part_rows, CatPlan& pl) {
+void cat_plan(int K, int n_cat, const int* n_levels, int64_t max_part_rows, CatPlan& pl) {
     pl.Ltot = 0;
     pl.npairs = 0;
     for (int c = 0; c < n_cat; ++c) {
         pl.npairs += pl.Ltot * n_levels[c];  // every earlier level x this column's levels
         pl.Ltot += n_levels[c];
     }
-    pl.NT = (pl.Ltot + 7) / 8;
-    pl.Lpad = pl.NT * 8;
-    pl.NTb = pl.NT <= 8 ? 8 : (pl.NT <= 16 ? 16 : 24);  // the register-tile bucket the kernel is compiled for
+    pl.Lpad = (pl.Ltot + 7) / 8 * 8;
     const int sms = cat_sm_count();
     int64_t S = K < sms ? sms / K : 1;
-    const int64_t s_rows = (max_part_rows + 2047) / 2048;  // at least 2048 rows per CTA
+    const int64_t s_rows = (max_part_rows + 4095) / 4096;  // at least 4096 rows per CTA
     if (S > s_rows) S = s_rows;
     const int64_t s_min = (max_part_rows + kCatMaxRowsPerCta - 1) / kCatMaxRowsPerCta;  // fixed-point headroom
     if (S < s_min) S = s_min;
     if (S < 1) S = 1;
     pl.S = (int)S;
-    pl.stride_d = 80 + (int64_t)pl.NTb * 64;
-    pl.stride_i = pl.Lpad + pl.npairs;
+    pl.stride_d = 80 + (int64_t)pl.Lpad * kTabPitch;
+    pl.stride_i = pl.npairs > 0 ? pl.npairs : 1;
     pl.bytes_d = (size_t)K * S * pl.stride_d * 8;
     pl.bytes_i = (size_t)K * S * pl.stride_i * 8;
-    return true;
+    // as many warps as shared memory allows (each owns a ring, a row scratch and a level table)
+    const size_t per_warp = (size_t)kCatStages * kStageBytes + kRowScratch + (size_t)pl.Lpad * kTabPitch * 8;
+    const size_t fixed = (size_t)(8 + pl.Lpad) * 8;
+    const size_t budget = 227 * 1024;
+    int warps = (int)((budget - fixed) / per_warp);
+    if (warps > kCatMaxWarps) warps = kCatMaxWarps;
+    pl.warps = warps;
+    pl.smem = (size_t)warps * per_warp + fixed;
 }
 
 }  // namespace
@@ -417,11 +460,11 @@ size_t irls_cat_workspace_bytes(int K, int n_cat, const int* n_levels, int64_t m
     return pl.bytes_d + pl.bytes_i + 256;
 }
 
-template <int NT, int NC>
-static int cat_launch_t(const CatArgs& a, size_t smem, cudaStream_t st) {
-    auto kern = irls_cat_kernel<NT, NC>;
-    DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<a.K * a.S, kCatThreads, smem, st>>>(a);
+template <int ROUNDS, int NC>
+static int cat_launch_t(const CatArgs& a, const CatPlan& pl, cudaStream_t st) {
+    auto kern = irls_cat_kernel<ROUNDS, NC>;
+    DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    kern<<<a.K * a.S, pl.warps * 32, pl.smem, st>>>(a);
     count_launch();
     return check_launch("irls_cat_kernel");
 }
@@ -432,7 +475,8 @@ int irls_cat_launch(const double* numeric, int64_t ldn, int n_num, const double*
                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
     CatPlan pl;
     cat_plan(K, n_cat, n_levels, max_part_rows, pl);
-    DLSA_REQUIRE(pl.NT <= 24, DLSA_E_UNSUPPORTED, "categorical pass: %d levels in total (max 192)", pl.Ltot);
+    DLSA_REQUIRE(pl.Ltot <= 192, DLSA_E_UNSUPPORTED, "categorical pass: %d levels in total (max 192)", pl.Ltot);
+    DLSA_REQUIRE(pl.warps >= 4, DLSA_E_UNSUPPORTED, "categorical pass: level tables do not fit shared memory");
     const size_t need = pl.bytes_d + pl.bytes_i + 256;
     DLSA_REQUIRE(workspace != nullptr && workspace_bytes >= need, DLSA_E_WORKSPACE,
                  "categorical pass: workspace %zu < %zu bytes", workspace_bytes, need);
@@ -471,13 +515,12 @@ int irls_cat_launch(const double* numeric, int64_t ldn, int n_num, const double*
     a.stride_d = pl.stride_d;
     a.stride_i = pl.stride_i;
     DLSA_CUDA(cudaMemsetAsync(a.part_i, 0, pl.bytes_i, st));
-    const int NTb = pl.NTb;
-    const size_t smem = (size_t)kCatWarps * kCatStages * kStageBytes + (size_t)(8 + pl.Lpad + 80 + NTb * 64) * 8;
-    int rc;
+    const int rounds = (9 * n_cat + 31) / 32;  // 1..3
     const bool c4 = n_cat <= 4;
-    if (NTb == 8) rc = c4 ? cat_launch_t<8, 4>(a, smem, st) : cat_launch_t<8, 8>(a, smem, st);
-    else if (NTb == 16) rc = c4 ? cat_launch_t<16, 4>(a, smem, st) : cat_launch_t<16, 8>(a, smem, st);
-    else rc = c4 ? cat_launch_t<24, 4>(a, smem, st) : cat_launch_t<24, 8>(a, smem, st);
+    int rc;
+    if (rounds == 1) rc = cat_launch_t<1, 4>(a, pl, st);
+    else if (rounds == 2) rc = c4 ? cat_launch_t<2, 4>(a, pl, st) : cat_launch_t<2, 8>(a, pl, st);
+    else rc = cat_launch_t<3, 8>(a, pl, st);
     if (rc != 0) return rc;
     irls_cat_finalize_kernel<<<K, 256, 0, st>>>(a, g, H, loglik);
     count_launch();

@@ -118,15 +118,10 @@ class ChunkMissingDummies(Exception):
         self.missing, self.shape = missing, shape
 
 
-def encode_design(sample_df, Y_name, dummy_info, dummy_factors_baseline, data_info, device, strict=True):
-    """Build the dense float64 design matrix of one chunk on the device in the reference layout.
-
-    Host side (strings): replace dropped levels by ``000_OTHERS`` (dlsa/models.py:60), map every categorical value
-    to the index of its ``<col>_<level>`` column (-1 for a baseline level).  Device side: kernel
-    ``dlsa_onehot_expand_f64`` writes the 1s and the (optionally standardised, :99-101) numerics.
-    Returns (X [n, px] cuda tensor, column names).  Raises ChunkMissingDummies when the chunk's dummy set differs
-    from the expected one (the caller turns it into the reference's warning + zero frame, :84-91); with
-    ``strict=False`` absent levels simply leave their columns at zero (logistic_model_eval, :189-197)."""
+def _encode_host(sample_df, Y_name, dummy_info, dummy_factors_baseline, data_info, strict):
+    """Host-side (string) part of the design encoding shared by the dense and the compact path: returns
+    (names, numeric columns, numeric ndarray [n, n_num], codes ndarray [n, n_cat] of ABSOLUTE column indices into
+    ``names`` (-1 = baseline level), categorical columns, (mean, std) ndarrays or None)."""
     has_dummies = dummy_info is not None and len(dummy_info) > 0
     names = design_columns(list(sample_df.columns), Y_name, dummy_info if has_dummies else None,
                            dummy_factors_baseline, False)
@@ -159,12 +154,30 @@ def encode_design(sample_df, Y_name, dummy_info, dummy_factors_baseline, data_in
         if present != set(names):
             raise ChunkMissingDummies(set(names) - present, (n, len(present)))
     num = np.ascontiguousarray(sample_df[numeric].to_numpy(dtype=np.float64)) if n_num else np.zeros((n, 0))
+    stats = None
+    if data_info is not None and len(data_info) > 0:
+        stats = (np.array([float(data_info[c][1]) for c in numeric]), np.array([float(data_info[c][2]) for c in numeric]))
+    return names, numeric, num, codes, conv, stats
+
+
+def encode_design(sample_df, Y_name, dummy_info, dummy_factors_baseline, data_info, device, strict=True):
+    """Build the dense float64 design matrix of one chunk on the device in the reference layout.
+
+    Host side (strings): replace dropped levels by ``000_OTHERS`` (dlsa/models.py:60), map every categorical value
+    to the index of its ``<col>_<level>`` column (-1 for a baseline level).  Device side: kernel
+    ``dlsa_onehot_expand_f64`` writes the 1s and the (optionally standardised, :99-101) numerics.
+    Returns (X [n, px] cuda tensor, column names).  Raises ChunkMissingDummies when the chunk's dummy set differs
+    from the expected one (the caller turns it into the reference's warning + zero frame, :84-91); with
+    ``strict=False`` absent levels simply leave their columns at zero (logistic_model_eval, :189-197)."""
+    names, numeric, num, codes, conv, stats = _encode_host(sample_df, Y_name, dummy_info, dummy_factors_baseline,
+                                                           data_info, strict)
+    n, n_num = sample_df.shape[0], len(numeric)
     X = torch.zeros(n, len(names), dtype=torch.float64, device=device)
     num_d = torch.as_tensor(num, device=device)
     mean_d = std_d = None
-    if data_info is not None and len(data_info) > 0:
-        mean_d = torch.as_tensor(np.array([float(data_info[c][1]) for c in numeric]), device=device)
-        std_d = torch.as_tensor(np.array([float(data_info[c][2]) for c in numeric]), device=device)
+    if stats is not None:
+        mean_d = torch.as_tensor(stats[0], device=device)
+        std_d = torch.as_tensor(stats[1], device=device)
     # numeric block occupies names[:n_num] (sorted numerics come first); codes are absolute column indices
     codes_d = torch.as_tensor(codes, device=device)
     base_d = torch.zeros(max(len(conv), 1), dtype=torch.int32, device=device)
@@ -175,3 +188,31 @@ def encode_design(sample_df, Y_name, dummy_info, dummy_factors_baseline, data_in
                                      base_d.data_ptr() if conv else None, n, X.data_ptr(), X.stride(0),
                                      torch.cuda.current_stream().cuda_stream), "dlsa_onehot_expand_f64")
     return X, names
+
+
+def encode_design_compact(sample_df, Y_name, dummy_info, dummy_factors_baseline, data_info, device, strict=True):
+    """The same design as ``encode_design`` in the COMPACT form the categorical pass K1c consumes
+    (``dlsa_irls_pass_cat_f64``): returns (numeric [n, n_num] cuda float64 (NOT yet standardised), codes [n, n_cat] cuda
+    int32 with the level's index inside its categorical block or -1, n_levels list, (mean, std) cuda tensors or
+    (None, None), column names).  The level blocks follow the numerics in ``names`` in ``dummy_columns`` order
+    (dlsa/models.py:71-79), which is exactly the column order K1c emits."""
+    names, numeric, num, codes, conv, stats = _encode_host(sample_df, Y_name, dummy_info, dummy_factors_baseline,
+                                                           data_info, strict)
+    n_num = len(numeric)
+    n_levels, start = [], n_num
+    for c in conv:
+        L = len([nm for nm in dummy_info["factor_selected_names"][c] if nm not in dummy_factors_baseline])
+        n_levels.append(L)
+        start += L
+    rel = codes.copy()
+    start = n_num
+    for ci, L in enumerate(n_levels):
+        col = rel[:, ci]
+        col[col >= 0] -= start
+        start += L
+    mean_d = std_d = None
+    if stats is not None:
+        mean_d = torch.as_tensor(stats[0], device=device)
+        std_d = torch.as_tensor(stats[1], device=device)
+    return (torch.as_tensor(num, device=device), torch.as_tensor(np.ascontiguousarray(rel), device=device), n_levels,
+            (mean_d, std_d), names)

@@ -12,7 +12,7 @@ import pandas as pd
 import torch
 
 from . import engine, synth
-from .dummies import ChunkMissingDummies, design_columns, encode_design
+from .dummies import ChunkMissingDummies, design_columns, encode_design, encode_design_compact
 from .lsa import _device
 
 
@@ -35,6 +35,38 @@ def _design(sample_df, Y_name, fit_intercept, dummy_info, dummy_factors_baseline
     return X, y, names
 
 
+def _compact_ok(sample_df, Y_name, dummy_info):
+    """True when the chunk's design fits the compact categorical pass K1c (<= 7 numerics, 1..8 dummy columns, <= 192
+    levels): the one-hot columns are then never materialised."""
+    if dummy_info is None or len(dummy_info) == 0:
+        return False
+    conv = list(dummy_info["factor_selected"].keys())
+    n_num = len(set(sample_df.columns) - {"partition_id", Y_name} - set(conv))
+    return engine.cat_supported(n_num, [len(dummy_info["factor_selected_names"][c]) for c in conv])
+
+
+def _fit_design(sample_df, Y_name, fit_intercept, dummy_info, dummy_factors_baseline, data_info, off_fn, config):
+    """Encode one frame and fit every partition ``off_fn`` cuts it into: the compact pass K1c when the design has dummy
+    blocks within its limits, else the dense pass K1 on the expanded matrix.  Returns (fits, names)."""
+    dev = _device()
+    y = torch.as_tensor(np.array(sample_df[Y_name].to_numpy(dtype=np.float64), copy=True), device=dev)
+    if _compact_ok(sample_df, Y_name, dummy_info):
+        num, codes, n_levels, (mean, std), names = encode_design_compact(sample_df, Y_name, dummy_info,
+                                                                          list(dummy_factors_baseline), data_info, dev)
+        if engine.cat_supported(num.shape[1], n_levels):
+            order, off = off_fn(dev)
+            if order is not None:
+                num, codes, y = num[order].contiguous(), codes[order].contiguous(), y[order].contiguous()
+            fits = engine.fit_logistic_partitions_cat(num if num.shape[1] else None, codes, n_levels, y, off,
+                                                      fit_intercept=fit_intercept, mean=mean, std=std, config=config)
+            return fits, names
+    X, names = encode_design(sample_df, Y_name, dummy_info, list(dummy_factors_baseline), data_info, dev)
+    order, off = off_fn(dev)
+    if order is not None:
+        X, y = X[order].contiguous(), y[order].contiguous()
+    return engine.fit_logistic_partitions(X, y, off, fit_intercept=fit_intercept, config=config), names
+
+
 def _frame(coef, smc, sig, names, par_id=None):
     p = coef.shape[0]
     out = pd.DataFrame(np.concatenate([coef[:, None], smc[:, None], sig], axis=1),
@@ -53,15 +85,15 @@ def logistic_model(sample_df, Y_name, fit_intercept=False, dummy_info=[], dummy_
     sklearn's exceptions and ConvergenceWarning in that situation)."""
     sample_df = sample_df.reset_index(drop=True)
     icpt = ["intercept"] if fit_intercept else []
+    n_rows = sample_df.shape[0]
     try:
-        X, y, names = _design(sample_df, Y_name, fit_intercept, dummy_info, dummy_factors_baseline, data_info)
+        fits, names = _fit_design(sample_df, Y_name, fit_intercept, dummy_info, dummy_factors_baseline, data_info,
+                                  lambda dev: (None, torch.tensor([0, n_rows], dtype=torch.int64, device=dev)), config)
     except ChunkMissingDummies as ex:
         names = design_columns(list(sample_df.columns), Y_name, dummy_info, dummy_factors_baseline, False)
         warnings.warn("Dummies:" + str(ex.missing) + "missing in this data chunk " + str(ex.shape)
                       + "Skip modeling this part of data.")
         return pd.DataFrame(0, index=np.arange(len(icpt + names)), columns=["par_id", "coef", "Sig_invMcoef"] + icpt + names)
-    off = torch.tensor([0, X.shape[0]], dtype=torch.int64, device=X.device)
-    fits = engine.fit_logistic_partitions(X, y, off, fit_intercept=fit_intercept, config=config)
     st = int(fits.status.item())
     if st != 0:
         raise ValueError(f"logistic_model: partition fit failed (status {st}: "
@@ -82,11 +114,17 @@ def logistic_model_partitions(data_df, Y_name, fit_intercept=False, dummy_info=[
     the tensor-level ``PartitionFits`` with ``return_fits=True``."""
     data_df = data_df.reset_index(drop=True)
     icpt = ["intercept"] if fit_intercept else []
-    X, y, names = _design(data_df, Y_name, fit_intercept, dummy_info, dummy_factors_baseline, data_info)
     pid_vals, pid_codes = np.unique(data_df["partition_id"].to_numpy(), return_inverse=True)
     K = len(pid_vals)
-    Xg, yg, off = synth.group_by_partition(X, y, torch.as_tensor(pid_codes, device=X.device), K)
-    fits = engine.fit_logistic_partitions(Xg, yg, off, fit_intercept=fit_intercept, config=config)
+
+    def by_partition(dev):  # the device-side repartition(K, "partition_id"): stable order inside a partition
+        pid = torch.as_tensor(pid_codes, device=dev).to(torch.int64)
+        off = torch.zeros(K + 1, dtype=torch.int64, device=dev)
+        off[1:] = torch.cumsum(torch.bincount(pid, minlength=K), 0)
+        return torch.argsort(pid, stable=True), off
+
+    fits, names = _fit_design(data_df, Y_name, fit_intercept, dummy_info, dummy_factors_baseline, data_info,
+                              by_partition, config)
     if return_fits:
         return fits, icpt + names
     coef, smc, sig = fits.coef.cpu().numpy(), fits.Sig_invMcoef.cpu().numpy(), fits.Sig_inv.cpu().numpy()

@@ -154,3 +154,45 @@ def test_cat_pass_rejects_unsupported_shapes(eng):
     with pytest.raises(DlsaLibraryError):  # 200 levels
         eng.irls_pass_cat(None, codes, [200], y, off, torch.zeros(1, 200, dtype=torch.float64, device="cuda"))
     assert not eng.cat_supported(8, [3]) and not eng.cat_supported(2, [100, 100]) and eng.cat_supported(7, [11, 6, 7, 75, 75])
+
+
+def test_facade_compact_route_equals_dense_route(eng, monkeypatch):
+    """logistic_model / logistic_model_partitions with dummy_info: the compact K1c route and the dense route (one-hot
+    expansion + K1) give the same frames — same columns, same numbers within solver tolerance."""
+    import pandas as pd
+    from dlsa_b200 import dummies, models
+    rng = np.random.default_rng(9)
+    n = 24_000
+    month = rng.integers(1, 13, n)
+    carrier = rng.choice(list("ABCDEFGH"), size=n, p=np.array([30, 20, 15, 12, 10, 6, 4, 3]) / 100.0)
+    znum, anum = rng.standard_normal(n) * 2 + 1, rng.standard_normal(n)
+    eta = -0.3 + 0.5 * anum - 0.2 * (znum - 1) / 2 + 0.2 * (month % 3) + 0.3 * (carrier == "B")
+    yv = (rng.random(n) < 1 / (1 + np.exp(-eta))).astype(float)
+    df = pd.DataFrame({"partition_id": (np.arange(n) % 3).astype(float), "y": yv, "znum": znum, "anum": anum,
+                       "Month": month, "Carrier": carrier})
+    info = dummies.select_dummy_factors(dummies.dummy_factors_counts(df, ["Month", "Carrier"]), [1, 0.8])
+    base = ["Month_1", "Carrier_000_OTHERS"]
+    desc = df[["anum", "znum"]].describe()
+    data_info = {c: desc[c].to_numpy() for c in ["anum", "znum"]}
+    calls = {"cat": 0}
+    real = eng.fit_logistic_partitions_cat
+
+    def spy(*a, **k):
+        calls["cat"] += 1
+        return real(*a, **k)
+
+    monkeypatch.setattr(eng, "fit_logistic_partitions_cat", spy)
+    compact = models.logistic_model_partitions(df, "y", fit_intercept=True, dummy_info=info, dummy_factors_baseline=base,
+                                               data_info=data_info)
+    one = models.logistic_model(df[df["partition_id"] == 1.0], "y", fit_intercept=True, dummy_info=info,
+                                dummy_factors_baseline=base, data_info=data_info)
+    assert calls["cat"] == 2
+    monkeypatch.setattr(eng, "cat_supported", lambda *a, **k: False)
+    dense = models.logistic_model_partitions(df, "y", fit_intercept=True, dummy_info=info, dummy_factors_baseline=base,
+                                             data_info=data_info)
+    assert calls["cat"] == 2
+    assert list(compact.columns) == list(dense.columns) and compact.shape == dense.shape
+    assert np.max(np.abs(compact["coef"].to_numpy() - dense["coef"].to_numpy())) < 1e-8
+    assert relfro(compact.iloc[:, 3:].to_numpy(), dense.iloc[:, 3:].to_numpy()) < 1e-10
+    p = one.shape[0]
+    assert np.max(np.abs(one["coef"].to_numpy() - compact["coef"].to_numpy()[p:2 * p])) < 1e-8
