@@ -332,6 +332,11 @@ def main():
                "config": {"workload": f"simulated logistic n={n:.0e} per GPU, p={p}, {K} partitions per GPU (configs[1])",
                           "rows_total": int(n_total), "partitions_total": K * world, "parallelism": f"partitions x{world}",
                           "newton_passes_per_step": fits.passes, "tol": 1e-10,
+                          "warm_start": {"pilot_partitions": fits.pilot_partitions, "pilot_passes": fits.pilot_passes,
+                                         "cold_restart": fits.cold_restart,
+                                         "note": "pilot block fitted from beta=0, its mean coefficients start the other "
+                                                 "partitions (R init.beta); same MLE, same tol; every pass is inside the "
+                                                 "timed region"},
                           "l2": "inputs (40.8 GB per pass) are far larger than the 126 MB L2; no flush needed",
                           "seed": args.seed},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -31,6 +31,15 @@ class EngineConfig:
     damp_above: float = 5.0
     damp_factor: float = 0.01
     want_loglik: bool = False   # True: one extra fused pass that also returns every partition's log-likelihood
+    # Pooled warm start (the R fitter takes ``init.beta``, dlsa/R/wlse_func.R:24,28): with >= warm_min_partitions
+    # partitions, a pilot block of the first max(pilot_min, K*pilot_fraction) partitions is fitted from 0 and the mean of
+    # its coefficients starts every other partition.  The MLE each partition converges to is the same (same tol); only
+    # the number of passes over X changes (C2: 6 -> 4 + the 1/32-size pilot).  Any partition the warm-started fit does not
+    # bring to ST_OK sends the whole batch through the cold start (beta = 0) the reference specifies.
+    warm_start: bool = True
+    warm_min_partitions: int = 64
+    pilot_fraction: float = 1.0 / 32.0
+    pilot_min: int = 8
 
 
 @dataclasses.dataclass
@@ -42,8 +51,11 @@ class PartitionFits:
     status: torch.Tensor        # [K] int32, _lib.ST_*
     iters: torch.Tensor         # [K] int32
     loglik: Optional[torch.Tensor]  # [K] at the returned coef (None if not requested)
-    passes: int                 # fused passes launched (Newton iterations + the final Sig_inv pass)
+    passes: int                 # fused passes launched over ALL partitions (Newton iterations; the last one's H is Sig_inv)
     n_rows: int
+    pilot_passes: int = 0       # passes over the pilot block only (pooled warm start), 0 when cold-started
+    pilot_partitions: int = 0
+    cold_restart: bool = False  # the warm-started fit left a partition unconverged and the batch was refitted from 0
 
 
 @dataclasses.dataclass
@@ -136,9 +148,11 @@ def irls_pass(X, y, part_offsets, beta, fit_intercept=False, family=_lib.FAMILY_
     return g, H, ll
 
 
-def _newton_fit(pass_fn, K: int, p: int, dev, cfg: EngineConfig, n_rows: int, beta_init=None) -> PartitionFits:
+def _newton_fit(pass_fn, K: int, p: int, dev, cfg: EngineConfig, n_rows: int, beta_init=None,
+                whole_batch: bool = True) -> PartitionFits:
     """The lock-step Newton loop shared by the dense and the categorical map: ``pass_fn(beta, active, out, want_loglik,
-    full)`` launches one fused pass (K1 / K1c) into ``out = (g, H, ll)``; K2 updates every active partition."""
+    full)`` launches one fused pass (K1 / K1c) into ``out = (g, H, ll)``; K2 updates every active partition.
+    ``whole_batch=False`` (pilot block) keeps its passes out of bench.py's full-pass timing."""
     beta = torch.zeros(K, p, dtype=_F64, device=dev) if beta_init is None else beta_init.to(dev, _F64).clone()
     g = torch.zeros(K, p, dtype=_F64, device=dev)
     H = torch.zeros(K, p, p, dtype=_F64, device=dev)
@@ -152,7 +166,7 @@ def _newton_fit(pass_fn, K: int, p: int, dev, cfg: EngineConfig, n_rows: int, be
     passes = 0
     left = K
     for _ in range(cfg.max_iter):
-        pass_fn(beta, active, (g, H, None), False, left == K)
+        pass_fn(beta, active, (g, H, None), False, whole_batch and left == K)
         passes += 1
         n_active.zero_()
         check(lib.dlsa_newton_update_f64(H.data_ptr(), g.data_ptr(), K, p, beta.data_ptr(), max_delta.data_ptr(),
@@ -178,9 +192,49 @@ def _newton_fit(pass_fn, K: int, p: int, dev, cfg: EngineConfig, n_rows: int, be
                          n_rows=n_rows)
 
 
+def _pooled_start(pilot: PartitionFits) -> Optional[torch.Tensor]:
+    """Mean coefficient vector of the pilot partitions that converged (None unless at least half of them did)."""
+    ok = pilot.status == _lib.ST_OK
+    n_ok = int(ok.sum().item())
+    if n_ok == 0 or 2 * n_ok < pilot.coef.shape[0]:
+        return None
+    return (pilot.coef * ok[:, None].to(_F64)).sum(0) / n_ok
+
+
+def _fit_warm(make_pass, part_offsets, K: int, p: int, dev, cfg: EngineConfig, n_rows: int, beta_init,
+              pooled_start=None) -> PartitionFits:
+    """Cold or pooled-warm-start Newton fit (EngineConfig.warm_start).  ``make_pass(offsets)`` returns the pass_fn over
+    the partitions ``offsets`` names (a prefix view of ``part_offsets`` for the pilot block: same X, same rows).
+    ``pooled_start`` [p]: a pooled coefficient vector from an earlier block of the same job (no pilot needed)."""
+    pilot_passes = Kp = 0
+    warm = False
+    if beta_init is None and pooled_start is not None and cfg.warm_start:
+        beta_init = pooled_start.to(dev, _F64).view(1, p).expand(K, p).clone()
+        warm = True
+    elif beta_init is None and cfg.warm_start and K >= max(2, cfg.warm_min_partitions):
+        Kp = min(K, max(int(cfg.pilot_min), int(K * cfg.pilot_fraction)))
+        pcfg = dataclasses.replace(cfg, want_loglik=False)
+        pilot = _newton_fit(make_pass(part_offsets[:Kp + 1]), Kp, p, dev, pcfg, 0, None, whole_batch=False)
+        pilot_passes = pilot.passes
+        start = _pooled_start(pilot)
+        if start is not None:
+            beta_init = start.expand(K, p).clone()
+            okp = (pilot.status == _lib.ST_OK)[:, None]
+            beta_init[:Kp] = torch.where(okp, pilot.coef, beta_init[:Kp])  # pilot partitions keep their own MLE
+            warm = True
+    fits = _newton_fit(make_pass(part_offsets), K, p, dev, cfg, n_rows, beta_init)
+    fits.pilot_passes, fits.pilot_partitions = pilot_passes, Kp
+    if warm and bool((fits.status != _lib.ST_OK).any().item()):
+        cold = _newton_fit(make_pass(part_offsets), K, p, dev, cfg, n_rows, None)
+        cold.passes += fits.passes
+        cold.pilot_passes, cold.pilot_partitions, cold.cold_restart = pilot_passes, Kp, True
+        fits = cold
+    return fits
+
+
 def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor, fit_intercept: bool = False,
-                            config: Optional[EngineConfig] = None, beta_init: Optional[torch.Tensor] = None
-                            ) -> PartitionFits:
+                            config: Optional[EngineConfig] = None, beta_init: Optional[torch.Tensor] = None,
+                            pooled_start: Optional[torch.Tensor] = None) -> PartitionFits:
     """Per-partition logistic MLE for every partition at once (the map side, dlsa/models.py:42-147).
 
     X [n, px] float64 row-major on the GPU with each partition's rows contiguous; ``part_offsets`` int64 [K+1].
@@ -195,13 +249,16 @@ def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torc
     p = px + (1 if fit_intercept else 0)
     sizes = part_offsets[1:] - part_offsets[:-1]
     max_rows = int(sizes.max().item()) if K > 0 else 0
-    ws_pass = _workspace(lib.dlsa_irls_pass_workspace_bytes(K, p, max_rows), dev)
 
-    def pass_fn(beta, active, out, want_ll, full):
-        irls_pass(X, y, part_offsets, beta, fit_intercept, _lib.FAMILY_LOGISTIC, active, max_rows,
-                  want_loglik=want_ll, out=out, workspace=ws_pass, full=full)
+    def make_pass(offsets):
+        ws_pass = _workspace(lib.dlsa_irls_pass_workspace_bytes(offsets.numel() - 1, p, max_rows), dev)
 
-    return _newton_fit(pass_fn, K, p, dev, cfg, int(X.shape[0]), beta_init)
+        def pass_fn(beta, active, out, want_ll, full):
+            irls_pass(X, y, offsets, beta, fit_intercept, _lib.FAMILY_LOGISTIC, active, max_rows,
+                      want_loglik=want_ll, out=out, workspace=ws_pass, full=full)
+        return pass_fn
+
+    return _fit_warm(make_pass, part_offsets, K, p, dev, cfg, int(X.shape[0]), beta_init, pooled_start)
 
 
 def _check_cat_inputs(numeric, codes, n_levels, y, part_offsets):
@@ -280,16 +337,20 @@ def fit_logistic_partitions_cat(numeric, codes, n_levels, y, part_offsets, fit_i
     max_rows = int(sizes.max().item()) if K > 0 else 0
     import ctypes as C
     nl = (C.c_int * len(n_levels))(*n_levels)
-    ws_pass = _workspace(lib.dlsa_irls_pass_cat_workspace_bytes(K, len(n_levels), nl, max_rows), dev)
     if mean is not None:
         mean = mean.to(dev, _F64).contiguous()
         std = std.to(dev, _F64).contiguous()
 
-    def pass_fn(beta, active, out, want_ll, full):
-        irls_pass_cat(numeric, codes, n_levels, y, part_offsets, beta, fit_intercept, mean, std, active, max_rows,
-                      want_loglik=want_ll, out=out, workspace=ws_pass, full=full)
+    def make_pass(offsets):
+        ws_pass = _workspace(lib.dlsa_irls_pass_cat_workspace_bytes(offsets.numel() - 1, len(n_levels), nl, max_rows),
+                             dev)
 
-    return _newton_fit(pass_fn, K, p, dev, cfg, int(codes.shape[0]), beta_init)
+        def pass_fn(beta, active, out, want_ll, full):
+            irls_pass_cat(numeric, codes, n_levels, y, offsets, beta, fit_intercept, mean, std, active, max_rows,
+                          want_loglik=want_ll, out=out, workspace=ws_pass, full=full)
+        return pass_fn
+
+    return _fit_warm(make_pass, part_offsets, K, p, dev, cfg, int(codes.shape[0]), beta_init)
 
 
 def fit_linear_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor) -> PartitionFits:
@@ -449,18 +510,24 @@ def dlsa_fit_host(Xh: torch.Tensor, yh: torch.Tensor, part_offsets_host: torch.T
             ev.record(copy)
             events.append(ev)
     parts = []
+    pooled = None  # mean coefficients of the first fitted block: the warm start of every later block
     for i in range(G):
         k0, k1 = bounds[i], bounds[i + 1]
         r0, r1 = offs[k0], offs[k1]
         off_g = (part_offsets_host[k0:k1 + 1] - r0).to(dev, non_blocking=True)
         compute.wait_event(events[i])
         if k1 > k0:
-            parts.append(fit_logistic_partitions(Xd[r0:r1], yd[r0:r1], off_g, fit_intercept, config))
+            parts.append(fit_logistic_partitions(Xd[r0:r1], yd[r0:r1], off_g, fit_intercept, config,
+                                                 pooled_start=pooled))
+            if pooled is None and K >= (config or EngineConfig()).warm_min_partitions:
+                pooled = _pooled_start(parts[-1])
     fits = PartitionFits(coef=torch.cat([f.coef for f in parts]), Sig_inv=torch.cat([f.Sig_inv for f in parts]),
                          Sig_invMcoef=torch.cat([f.Sig_invMcoef for f in parts]),
                          status=torch.cat([f.status for f in parts]), iters=torch.cat([f.iters for f in parts]),
                          loglik=None if parts[0].loglik is None else torch.cat([f.loglik for f in parts]),
-                         passes=max(f.passes for f in parts), n_rows=int(n))
+                         passes=max(f.passes for f in parts), n_rows=int(n),
+                         pilot_passes=parts[0].pilot_passes, pilot_partitions=parts[0].pilot_partitions,
+                         cold_restart=any(f.cold_restart for f in parts))
     comb = combine_partitions(fits, group=group)
     if sample_size is None:
         nt = torch.tensor([float(n)], dtype=_F64, device=dev)
