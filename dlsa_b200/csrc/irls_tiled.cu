@@ -10,19 +10,21 @@
 //     bitwise reproducible.  A diagonal block is PARTIAL (only tiles on or below the diagonal exist): a warp gets
 //     at most one, in its last slot, and runs a body compiled for that block's shape — a predicated-off DMMA
 //     still occupies the FP64 pipe for its 16 cycles (measured), so masking by predicate is not an option.
-//   * All heavy FP64 work lives in the 12 MMA warps (setmaxnreg 152), interleaved with their DMMAs where it costs
-//     only its pipe cycles: the Gram blocks; g = X'r (4 DFMAs per k-step in the warp that owns a column group's
-//     diagonal block, reusing its B fragments; the intercept column is an ordinary column of ones in shared
-//     memory); and the partial dot products of eta = x'beta for a chunk a few ahead (lane = column stripe, 4 rows
-//     in flight, transposed butterfly).  A scalar FP64 instruction issued from a separate warp waits its
-//     round-robin turn behind the DMMA streams (~50 cycles, measured): per-row work there must be tiny.
-//   * 3 link warps take whole chunks round-robin: one sigmoid per lane for the 16 rows of a chunk (w, r, the
-//     log-likelihood, the padding-column repair for odd px), nothing else.  1 producer warp keeps a ring of
-//     16-row chunks full with one TMA bulk copy per row (UBLKCP; rows land with a pitch == 4 mod 16 doubles so
-//     that fragment loads are bank-conflict free).  Stages are gated by full / eta / wr / empty mbarriers.
+//   * The 12 MMA warps (setmaxnreg 152) do the Gram blocks and g = X'r (4 DFMAs per k-step in the warp that owns a column
+//     group's diagonal block, reusing its B fragments; the intercept column is an ordinary column of ones in shared
+//     memory) and nothing else: their loop is wait(full, wr) -> straight-line DMMA body -> arrive(empty).
+//   * 3 link warps take whole chunks round-robin and run AHEAD of the MMA warps by up to the ring depth: eta = x'beta of
+//     one row per lane (two columns per LDS.128, rotated so a quarter-warp wavefront is conflict-free), the sigmoid,
+//     w, r, the log-likelihood, the padding-column repair for odd px.  (The previous version computed the eta partial
+//     sums inside the MMA warps, LA chunks ahead: ncu showed them spending 18 % of their time there on a 2 000-cycle
+//     serial stretch per call and the link warps idle 91 % of the time — profiles/r01_k1_tiled_p100_logit_before.md.)
+//     1 producer warp keeps a ring of 16- or 32-row chunks full with one TMA bulk copy per row (UBLKCP; rows land with
+//     a pitch == 4 mod 16 doubles so that fragment loads are bank-conflict free).  Stages are gated by full / wr / empty
+//     mbarriers.
 //   * Sibling CTAs (tile group tg = blockIdx.x % TG) are adjacent in the grid, run at the same time and read the
 //     same rows: X comes from HBM once and from L2 TG-1 times.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include <vector>
 
@@ -34,7 +36,9 @@ constexpr int kTMma = 12;                       // MMA warps
 constexpr int kTLink = 3;                       // link (sigmoid) warps
 constexpr int kTWarps = kTMma + kTLink + 1;     // + producer = 16; setmaxnreg acts on whole warpgroups (4 aligned warps)
 constexpr int kTThreads = kTWarps * 32;         // 512 -> 128 registers per thread at launch
-constexpr int kTCH = 16;                        // rows per chunk
+// rows per chunk: 32 when at least 4 stages of 32 rows fit in shared memory (p <= ~200), else 16.  The per-chunk costs of
+// an MMA warp (barrier waits, stage bookkeeping, the switch into its body, its share of the eta partial sums) are ~40 % of
+// a 16-row chunk's time at p=100 (ncu, profiles/r01_k1_tiled_p100_logit_*): 32-row chunks halve them per row.
 constexpr int kTMaxTG = 16;
 constexpr int kTNBW = 3;                        // block slots per MMA warp
 constexpr int kTRegsMma = 152;
@@ -62,7 +66,10 @@ struct TiledArgs {
     double* outH;   // [K*S][p*p]
     double* outg;   // [K*S][p]
     double* outll;  // [K*S] or nullptr
-    int K, px, p, icpt, S, Sd, aligned, want_ll, NT, TG, stages, copy_cols, lookahead;
+    const double* pre_w;   // PRE mode: w, r (and the per-row log-likelihood terms) of every row, written by
+    const double* pre_r;   // tiled_link_kernel, indexed by global row
+    const double* pre_ll;
+    int K, px, p, icpt, S, Sd, aligned, want_ll, NT, TG, stages, copy_cols;
     // block of MMA warp w, slot b of sibling tg: bits 0-7 valid-tile mask (bit 4*ii+jj), 8-15 row pair m, 16-23 column
     // group J, 24 g-owner flag, 25-27 partial pattern; 0 = empty slot.  Full blocks first, the partial one last.
     uint32_t sched[kTMaxTG * kTMma * kTNBW];
@@ -76,15 +83,17 @@ __device__ __forceinline__ void t_mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// The 4 k-steps of one chunk for an MMA warp that owns NF full blocks and (PAT != kPatNone) one partial block.
-template <bool LOGIT, int NF, int PAT>
+// 4 k-steps (16 rows) of a chunk for an MMA warp that owns NF full blocks and (PAT != kPatNone) one partial block.
+template <bool LOGIT, int NF, int PAT, int NH>
 __device__ __forceinline__ void tiled_chunk_body(const double* __restrict__ T, const double* __restrict__ ws,
                                                  const double* __restrict__ rs, int Sd, const int (&offA)[kTNBW],
                                                  const int (&offB)[kTNBW], bool has_g, double (&C)[kTNBW][2][4][2],
                                                  double (&gacc)[4]) {
     constexpr int N0 = pat_n0(PAT), N1 = pat_n1(PAT);
+#pragma unroll 1
+    for (int hb = 0; hb < NH; hb++, T += (size_t)16 * Sd, ws += 16, rs += 16)
 #pragma unroll
-    for (int ks = 0; ks < kTCH / 4; ks++) {
+    for (int ks = 0; ks < 4; ks++) {
         const double wv = LOGIT ? ws[4 * ks] : 1.0;
         const double* Tr = T + (size_t)(4 * ks) * Sd;  // row 4ks + q
 #pragma unroll
@@ -121,7 +130,7 @@ __device__ __forceinline__ void tiled_chunk_body(const double* __restrict__ T, c
     }
 }
 
-template <int FAMILY>
+template <int FAMILY, int kTCH, bool PRE>
 __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_constant__ TiledArgs a) {
     constexpr bool LOGIT = FAMILY == DLSA_FAMILY_LOGISTIC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -131,7 +140,7 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
     const int k = item / a.S, slice = item % a.S;
     if (a.active != nullptr && a.active[k] == 0) return;
 
-    const int p = a.p, px = a.px, Sd = a.Sd, ST = a.stages, LA = a.lookahead;
+    const int p = a.p, px = a.px, Sd = a.Sd, ST = a.stages;
     const int64_t row_lo = a.part_off[k];
     const int64_t n_k = a.part_off[k + 1] - row_lo;
     const int64_t nchunks = (n_k + kTCH - 1) / kTCH;
@@ -141,21 +150,19 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
     const int my_n = (c_hi > c_lo) ? (int)(c_hi - c_lo) : 0;
 
     // ---- shared memory: tiles [ST][CH*Sd] | ws, rs, eta [ST][CH] each | beta_s [Sd] | llred [4] | bars [ST][4]
+    // (beta_s holds the feature coefficients only: 0 at the intercept / padding columns, so the eta partial sums
+    // can run over whole 32-column stripes without a bounds test; the intercept coefficient is added as b0)
     const int stage_doubles = kTCH * Sd;
     double* tiles = reinterpret_cast<double*>(smem_raw);
     double* ws_all = tiles + (size_t)ST * stage_doubles;
     double* rs_all = ws_all + ST * kTCH;
-    double* eta_all = rs_all + ST * kTCH;
-    double* beta_s = eta_all + ST * kTCH;
+    double* beta_s = rs_all + ST * kTCH;
     double* llred = beta_s + Sd;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(llred + 4);  // [ST][4]: full, wr, empty, eta
+    uint64_t* bars = reinterpret_cast<uint64_t*>(llred + 4);  // [ST][4]: full, wr, empty, (unused)
 
     for (int c = tid; c < Sd; c += kTThreads) {
         double bv = 0.0;
-        if (LOGIT) {
-            if (c < px) bv = a.beta[(size_t)k * p + c + a.icpt];
-            else if (c == px && a.icpt) bv = a.beta[(size_t)k * p];
-        }
+        if (LOGIT && c < px) bv = a.beta[(size_t)k * p + c + a.icpt];
         beta_s[c] = bv;
     }
     // zero the ring once (tail chunks leave stale finite rows behind, never uninitialised ones; columns >= px are
@@ -169,7 +176,6 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
         mbar_init(smem_u32(&b[0]), a.aligned ? 1u : 32u);
         mbar_init(smem_u32(&b[1]), 1u);               // the link warp that owns the chunk
         mbar_init(smem_u32(&b[2]), (uint32_t)kTMma);
-        mbar_init(smem_u32(&b[3]), 4u);               // the 4 MMA warps of the chunk's eta group
         fence_mbar_init();
     }
     fence_proxy_async();
@@ -211,16 +217,34 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
         // =========================== link warps: sigmoid, w, r, log-likelihood; one row per lane ============
         t_setmaxnreg_dec<kTRegsAux>();
         const int lw = warp - kTMma;            // takes chunks ci == lw (mod 3)
-        const int row = lane & 15;
-        const bool act = lane < 16;
+        const int row = lane & (kTCH - 1);
+        const bool act = lane < kTCH;
         const bool fix_pad = a.copy_cols > px;  // odd px: the copy drags one foreign column along
         const double pad_val = a.icpt ? 1.0 : 0.0;
+        // eta = x'beta of this lane's row (CH = 32) or half row (CH = 16: lanes l and l+16 share row l), two columns per
+        // LDS.128.  The 8 lanes of a quarter-warp wavefront read rows 8 doubles apart modulo 32 banks (Sd == 4 mod 16), so
+        // rows 4..7 of each octet start one column pair later (rotation inside the lane's pair range): conflict-free.
+        const int npairs = (px + 1) / 2;
+        const int nparts = 32 / kTCH;
+        const int per_part = (npairs + nparts - 1) / nparts;
+        const int pb = (lane / kTCH) * per_part;
+        const int plen = (npairs - pb < per_part) ? (npairs - pb) : per_part;
+        const int skew = (row >> 2) & 1;
+        const double b0 = (LOGIT && a.icpt) ? a.beta[(size_t)k * p] : 0.0;
         double llacc = 0.0;
         auto load_y = [&](int ci) -> double {
             const int64_t r = (c_lo + ci) * kTCH + row;
             return (ci < my_n && r < n_k) ? __ldg(yp + r) : 0.0;
         };
-        double y_next = load_y(lw);
+        // PRE: the link stage ran as its own kernel; this warp only moves w, r (and the log-likelihood terms) of its
+        // chunk from global to shared memory
+        auto load_pre = [&](const double* src, int ci) -> double {
+            const int64_t r = (c_lo + ci) * kTCH + row;
+            return (ci < my_n && r < n_k) ? __ldg(src + row_lo + r) : 0.0;
+        };
+        double y_next = PRE ? 0.0 : load_y(lw);
+        double w_next = PRE ? load_pre(a.pre_w, lw) : 0.0, r_next = PRE ? load_pre(a.pre_r, lw) : 0.0;
+        double l_next = (PRE && a.want_ll) ? load_pre(a.pre_ll, lw) : 0.0;
         int st = lw % ST;
         uint32_t par = (uint32_t)((lw / ST) & 1);
         for (int ci = lw; ci < my_n; ci += kTLink) {
@@ -228,11 +252,36 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
             const int valid = (n_k - r0 < kTCH) ? (int)(n_k - r0) : kTCH;
             const bool rowvalid = act && row < valid;
             const double yv = y_next;
-            y_next = load_y(ci + kTLink);
+            if (!PRE) y_next = load_y(ci + kTLink);
             double wv, rv;
-            if (LOGIT) {
-                mbar_wait(smem_u32(&bars[st * 4 + 3]), par);  // eta of the chunk's 16 rows is in shared memory
-                const double eta = eta_all[st * kTCH + row];
+            if (PRE) {
+                wv = w_next;
+                rv = r_next;
+                if (rowvalid) llacc += l_next;
+                w_next = load_pre(a.pre_w, ci + kTLink);
+                r_next = load_pre(a.pre_r, ci + kTLink);
+                if (a.want_ll) l_next = load_pre(a.pre_ll, ci + kTLink);
+                mbar_wait(smem_u32(&bars[st * 4 + 0]), par);  // the stage belongs to this chunk now
+            } else if (LOGIT) {
+                mbar_wait(smem_u32(&bars[st * 4 + 0]), par);  // rows landed
+                const double* Tr = tiles + (size_t)st * stage_doubles + (size_t)row * Sd + 2 * pb;
+                const double* bp = beta_s + 2 * pb;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int pj = skew < plen ? skew : 0;
+#pragma unroll 2
+                for (int j = 0; j < per_part; j++) {
+                    if (j < plen) {
+                        double2 xv = *reinterpret_cast<const double2*>(Tr + 2 * pj);
+                        const double2 bv = *reinterpret_cast<const double2*>(bp + 2 * pj);
+                        if (2 * (pb + pj) + 1 == px) xv.y = 0.0;  // the padding column of an odd px may hold anything
+                        if (j & 1) { a2 = fma(xv.x, bv.x, a2); a3 = fma(xv.y, bv.y, a3); }
+                        else       { a0 = fma(xv.x, bv.x, a0); a1 = fma(xv.y, bv.y, a1); }
+                        if (++pj == plen) pj = 0;
+                    }
+                }
+                double eta = (a0 + a1) + (a2 + a3);
+                if (kTCH == 16) eta += shfl_xor_f64(eta, 16);
+                eta += b0;
                 const double e = exp_nonpos(-fabs(eta));
                 const double pr = div_pos((eta >= 0.0) ? 1.0 : e, 1.0 + e);
                 wv = pr * (1.0 - pr);
@@ -257,7 +306,7 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
         }
         if (tg == 0 && a.outll != nullptr) {
 #pragma unroll
-            for (int m = 8; m >= 1; m >>= 1) llacc += shfl_xor_f64(llacc, m);  // lanes 0..15 hold the rows
+            for (int m = kTCH / 2; m >= 1; m >>= 1) llacc += shfl_xor_f64(llacc, m);  // lanes 0..CH-1 hold the rows
             if (lane == 0) llred[lw] = llacc;
             asm volatile("bar.sync 1, 96;" ::: "memory");
             if (lw == 0 && lane == 0) a.outll[item] = (llred[0] + llred[1]) + llred[2];
@@ -285,59 +334,23 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
                 for (int jj = 0; jj < 4; jj++) C[b][ii][jj][0] = C[b][ii][jj][1] = 0.0;
         double gacc[4] = {0.0, 0.0, 0.0, 0.0};
 
-        // eta partial sums: the 4 warps with warp/4 == g handle the chunks == g (mod 3), warp%4 picks the 4-row batch
-        const int egrp = warp >> 2, ebatch = warp & 3;
-        const int bit4 = (lane >> 4) & 1, bit3 = (lane >> 3) & 1;
-        const int jn = (px + 31) / 32;
-        const double b0 = (LOGIT && a.icpt) ? beta_s[px] : 0.0;
-        auto eta_chunk = [&](int st_e, uint32_t par_e) {
-            mbar_wait(smem_u32(&bars[st_e * 4 + 0]), par_e);
-            const double* Tb = tiles + (size_t)st_e * stage_doubles + (size_t)(ebatch * 4) * Sd + lane;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            for (int j = 0; j < jn; j++) {
-                const int c = lane + 32 * j;
-                if (c < px) {
-                    const double bv = beta_s[c];
-                    s0 = fma(Tb[32 * j], bv, s0);
-                    s1 = fma(Tb[32 * j + Sd], bv, s1);
-                    s2 = fma(Tb[32 * j + 2 * Sd], bv, s2);
-                    s3 = fma(Tb[32 * j + 3 * Sd], bv, s3);
-                }
-            }
-            // transposed butterfly: 4 rows x 32 lanes -> every group of 8 lanes holds one row's sum
-            const double t0 = (bit4 ? s2 : s0) + shfl_xor_f64(bit4 ? s0 : s2, 16);
-            const double t1 = (bit4 ? s3 : s1) + shfl_xor_f64(bit4 ? s1 : s3, 16);
-            double u = (bit3 ? t1 : t0) + shfl_xor_f64(bit3 ? t0 : t1, 8);
-            u += shfl_xor_f64(u, 4);
-            u += shfl_xor_f64(u, 2);
-            u += shfl_xor_f64(u, 1);
-            if ((lane & 7) == 0) eta_all[st_e * kTCH + ebatch * 4 + 2 * bit4 + bit3] = u + b0;
-            __syncwarp();
-            if (lane == 0) t_mbar_arrive(smem_u32(&bars[st_e * 4 + 3]));
-        };
+        const uint32_t bars_u32 = smem_u32(bars);
 
         // Per chunk: ONE shared loop (barriers, stage counters, eta) and a switch into the k-step body compiled for
         // this warp's (number of full blocks, shape of the partial block).  The bodies are straight-line code with
         // unconditional fragment loads (every column a block can name exists in shared memory); sharing the rest
         // keeps the instruction footprint of the 12 MMA warps inside the 32 KB instruction cache.
         const int path = pat * 4 + nfull;
-        int st = 0, st_e = 0, eg = 0;  // stage of chunk ci; stage and eta group of chunk ci + LA
-        uint32_t par = 0, par_e = 0;
-        if (LOGIT) {
-            for (int ce = 0; ce < LA; ce++) {
-                if (ce < my_n && eg == egrp) eta_chunk(st_e, par_e);
-                if (++st_e == ST) { st_e = 0; par_e ^= 1u; }
-                if (++eg == 3) eg = 0;
-            }
-        }
+        int st = 0;
+        uint32_t par = 0;
         for (int ci = 0; ci < my_n; ci++) {
-            mbar_wait(smem_u32(&bars[st * 4 + 0]), par);  // rows landed (async-proxy writes visible here)
-            mbar_wait(smem_u32(&bars[st * 4 + 1]), par);  // w, r written, pad column repaired
+            mbar_wait(bars_u32 + (uint32_t)(st * 4 + 0) * 8u, par);  // rows landed (async-proxy writes visible here)
+            mbar_wait(bars_u32 + (uint32_t)(st * 4 + 1) * 8u, par);  // w, r written, pad column repaired
             const double* T = tiles + (size_t)st * stage_doubles + (size_t)q * Sd;
             const double* ws = ws_all + st * kTCH + q;
             const double* rs = rs_all + st * kTCH + q;
 #define DLSA_BODY(NF_, PAT_) \
-    case (PAT_) * 4 + (NF_): tiled_chunk_body<LOGIT, NF_, PAT_>(T, ws, rs, Sd, offA, offB, has_g, C, gacc); break;
+    case (PAT_) * 4 + (NF_): tiled_chunk_body<LOGIT, NF_, PAT_, kTCH / 16>(T, ws, rs, Sd, offA, offB, has_g, C, gacc); break;
             switch (path) {
                 DLSA_BODY(0, kPatNone) DLSA_BODY(1, kPatNone) DLSA_BODY(2, kPatNone) DLSA_BODY(3, kPatNone)
                 DLSA_BODY(0, kPat34) DLSA_BODY(1, kPat34) DLSA_BODY(2, kPat34)
@@ -349,13 +362,8 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
             }
 #undef DLSA_BODY
             __syncwarp();
-            if (lane == 0) t_mbar_arrive(smem_u32(&bars[st * 4 + 2]));  // done with the stage
+            if (lane == 0) t_mbar_arrive(bars_u32 + (uint32_t)(st * 4 + 2) * 8u);  // done with the stage
             if (++st == ST) { st = 0; par ^= 1u; }
-            if (LOGIT) {
-                if (ci + LA < my_n && eg == egrp) eta_chunk(st_e, par_e);
-                if (++st_e == ST) { st_e = 0; par_e ^= 1u; }
-                if (++eg == 3) eg = 0;
-            }
         }
 
         // ---- emit: every tile (and every column of g) has exactly one owner -------------------------------------
@@ -420,9 +428,85 @@ __global__ void slice_reduce_tiled_kernel(const double* __restrict__ pH, const d
     }
 }
 
+// The link stage as its own streaming kernel (PRE mode, used when the Gram needs sibling CTAs or p is large): for every
+// row eta = x'beta_k, prob = sigmoid(eta), w = prob(1-prob), r = y - prob and the log-likelihood term, written to
+// w[n], r[n], ll[n] (global row index).  With TG sibling CTAs per partition slice the fused link stage is computed TG
+// times over, by 3 warps per CTA whose FP64 instructions queue behind 12 DMMA streams (~100 cycles each, measured): at
+// p = 500 that is slower than reading X a second time at HBM speed.  One warp takes 32 rows: 8 batches of 4 rows with
+// lane = column stripe (coalesced), a transposed butterfly per batch, then ONE sigmoid per lane for the 32 rows.
+constexpr int kLinkWarps = 8;
+__global__ void __launch_bounds__(kLinkWarps * 32) tiled_link_kernel(const double* __restrict__ X, int64_t ldx,
+                                                                     const double* __restrict__ y,
+                                                                     const int64_t* __restrict__ part_off,
+                                                                     const double* __restrict__ beta,
+                                                                     const int* __restrict__ active, int px, int icpt,
+                                                                     double* __restrict__ wout, double* __restrict__ rout,
+                                                                     double* __restrict__ llout) {
+    extern __shared__ double link_s[];  // beta [32 * jn] | eta [kLinkWarps][32]
+    const int k = blockIdx.y;
+    if (active != nullptr && active[k] == 0) return;
+    const int p = px + icpt;
+    const int jn = (px + 31) / 32;
+    double* beta_s = link_s;
+    double* eta_s = link_s + 32 * jn;
+    for (int c = threadIdx.x; c < 32 * jn; c += blockDim.x) beta_s[c] = (c < px) ? beta[(size_t)k * p + c + icpt] : 0.0;
+    __syncthreads();
+    const double b0 = icpt ? beta[(size_t)k * p] : 0.0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bit4 = (lane >> 4) & 1, bit3 = (lane >> 3) & 1;
+    const int64_t row_lo = part_off[k];
+    const int64_t n_k = part_off[k + 1] - row_lo;
+    const double* Xp = X + row_lo * ldx;
+    for (int64_t base = ((int64_t)blockIdx.x * kLinkWarps + warp) * 32; base < n_k;
+         base += (int64_t)gridDim.x * kLinkWarps * 32) {
+#pragma unroll 1
+        for (int b = 0; b < 8; b++) {
+            const int64_t r = base + 4 * b;
+            if (r >= n_k) break;  // warp-uniform
+            const double* x0 = Xp + r * ldx + lane;
+            // rows past the end of the partition re-read its last row: finite values, results discarded
+            const int64_t last = n_k - 1 - r;
+            const double* x1 = x0 + (last >= 1 ? 1 : last) * ldx;
+            const double* x2 = x0 + (last >= 2 ? 2 : last) * ldx;
+            const double* x3 = x0 + (last >= 3 ? 3 : last) * ldx;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 2
+            for (int j = 0; j < jn; j++) {
+                const bool in = lane + 32 * j < px;
+                const double bv = beta_s[lane + 32 * j];
+                const double v0 = in ? __ldg(x0 + 32 * j) : 0.0, v1 = in ? __ldg(x1 + 32 * j) : 0.0;
+                const double v2 = in ? __ldg(x2 + 32 * j) : 0.0, v3 = in ? __ldg(x3 + 32 * j) : 0.0;
+                s0 = fma(v0, bv, s0);
+                s1 = fma(v1, bv, s1);
+                s2 = fma(v2, bv, s2);
+                s3 = fma(v3, bv, s3);
+            }
+            const double t0 = (bit4 ? s2 : s0) + shfl_xor_f64(bit4 ? s0 : s2, 16);
+            const double t1 = (bit4 ? s3 : s1) + shfl_xor_f64(bit4 ? s1 : s3, 16);
+            double u = (bit3 ? t1 : t0) + shfl_xor_f64(bit3 ? t0 : t1, 8);
+            u += shfl_xor_f64(u, 4);
+            u += shfl_xor_f64(u, 2);
+            u += shfl_xor_f64(u, 1);
+            if ((lane & 7) == 0) eta_s[warp * 32 + 4 * b + 2 * bit4 + bit3] = u;
+        }
+        __syncwarp();
+        const int64_t r = base + lane;
+        if (r < n_k) {
+            const double eta = eta_s[warp * 32 + lane] + b0;
+            const double yv = __ldg(y + row_lo + r);
+            const double e = exp_nonpos(-fabs(eta));
+            const double pr = div_pos((eta >= 0.0) ? 1.0 : e, 1.0 + e);
+            wout[row_lo + r] = pr * (1.0 - pr);
+            rout[row_lo + r] = yv - pr;
+            if (llout != nullptr) llout[row_lo + r] = yv * eta - (fmax(eta, 0.0) + log1p_01(e));
+        }
+        __syncwarp();
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 struct TiledCfg {
-    int NT, TG, Sd, stages, lookahead;
+    int NT, TG, Sd, stages, CH, pre;
     size_t smem;
     std::vector<uint32_t> sched;
 };
@@ -532,20 +616,30 @@ static TiledCfg tiled_cfg(int px, int p) {
     c.Sd = cols;
     while (c.Sd % 16 != 4) c.Sd++;
     const size_t fixed = ((size_t)c.Sd + 4) * 8 + 256;
-    const size_t per_stage = ((size_t)kTCH * c.Sd + 3 * kTCH) * 8 + 4 * 8;
+    auto stage_bytes = [&](int ch) { return ((size_t)ch * c.Sd + 2 * ch) * 8 + 4 * 8; };
+    c.CH = 32;
+    if ((220 * 1024 - fixed) / stage_bytes(32) < 3) c.CH = 16;
+    if (const char* ev = std::getenv("DLSA_TILED_CH")) {  // tuning override (tools/k1_sweep.py): 16 or 32
+        const int v = std::atoi(ev);
+        if (v == 16 || (v == 32 && (220 * 1024 - fixed) / stage_bytes(32) >= 3)) c.CH = v;
+    }
+    // link stage: fused into the Gram kernel while one CTA holds the whole triangle, as a streaming kernel of its own
+    // (X read twice, the second time far below the FP64 time of the Gram) once sibling CTAs would each repeat it
+    c.pre = c.TG >= 2 ? 1 : 0;
+    if (const char* ev = std::getenv("DLSA_TILED_PRE")) c.pre = std::atoi(ev) ? 1 : 0;  // tuning override
+    const size_t per_stage = stage_bytes(c.CH);
     int st = (int)((220 * 1024 - fixed) / per_stage);
-    c.stages = st > 12 ? 12 : st;
-    // chunks between the eta partial sums of a chunk and the DMMAs that need its w: the link warp needs ~2 chunk times,
-    // and the rows of chunk ci+LA must have landed, i.e. ST-LA chunk times must cover the HBM latency
-    c.lookahead = (c.stages - 1) / 2;
-    if (c.lookahead > 5) c.lookahead = 5;
-    if (c.lookahead < 2) c.lookahead = 2;
+    // A multiple of 3 (the number of link warps): link warp l then owns the stages == l (mod 3) and sees every phase of
+    // their barriers in order.  With any other ring size a link warp comes round to a stage whose previous phase belongs
+    // to another link warp's chunk and may still be pending: a parity wait cannot tell "not yet" from "one phase ahead".
+    st = st > 12 ? 12 : st - st % 3;
+    c.stages = st;
     c.smem = fixed + per_stage * c.stages;
     return c;
 }
 
-static int tiled_slices(int K, int TG, int64_t max_part_rows) {
-    const int64_t chunks = (max_part_rows + kTCH - 1) / kTCH;
+static int tiled_slices(int K, int TG, int CH, int64_t max_part_rows) {
+    const int64_t chunks = (max_part_rows + CH - 1) / CH;
     int64_t s_cap = chunks / 8;
     if (s_cap < 1) s_cap = 1;
     if (s_cap > 32) s_cap = 32;
@@ -560,12 +654,18 @@ static int tiled_slices(int K, int TG, int64_t max_part_rows) {
     return best_s;
 }
 
+static size_t tiled_slice_bytes(int K, int S, int p) {
+    return S == 1 ? 0 : (size_t)K * S * ((size_t)p * p + p + 1) * sizeof(double);
+}
+
+// workspace = [slice partials | w, r, ll of every row (PRE mode; rows <= K * max_part_rows)]
 size_t irls_tiled_workspace_bytes(int K, int p, int64_t max_part_rows) {
     if (p > kTiledMaxP) return 0;
     TiledCfg c = tiled_cfg(p, p);
-    const int S = tiled_slices(K, c.TG, max_part_rows);
-    if (S == 1) return 0;
-    return (size_t)K * S * ((size_t)p * p + p + 1) * sizeof(double);
+    const int S = tiled_slices(K, c.TG, c.CH, max_part_rows);
+    size_t need = tiled_slice_bytes(K, S, p);
+    if (c.pre) need += 3 * (size_t)K * (size_t)max_part_rows * sizeof(double);
+    return need;
 }
 
 int irls_tiled_launch(const double* X, int64_t ldx, const double* y, const int64_t* part_off, int K, int px, int icpt,
@@ -576,37 +676,61 @@ int irls_tiled_launch(const double* X, int64_t ldx, const double* y, const int64
     TiledCfg c = tiled_cfg(px, p);
     DLSA_REQUIRE(c.TG <= kTMaxTG && c.stages >= 3, DLSA_E_UNSUPPORTED, "irls pass: p=%d does not fit (TG=%d, stages=%d)",
                  p, c.TG, c.stages);
-    const int S = tiled_slices(K, c.TG, max_part_rows);
+    const int S = tiled_slices(K, c.TG, c.CH, max_part_rows);
     TiledArgs a;
     a.X = X; a.ldx = ldx; a.y = y; a.part_off = part_off; a.beta = beta; a.active = active;
     a.K = K; a.px = px; a.p = p; a.icpt = icpt ? 1 : 0; a.S = S; a.Sd = c.Sd;
-    a.want_ll = loglik != nullptr; a.NT = c.NT; a.TG = c.TG; a.stages = c.stages; a.lookahead = c.lookahead;
+    a.want_ll = loglik != nullptr; a.NT = c.NT; a.TG = c.TG; a.stages = c.stages;
     // one 16-byte-aligned bulk copy per row: even row pitch; an odd px drags the next (padding) column along
     a.aligned = ((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (ldx % 2) == 0) ? 1 : 0;
     a.copy_cols = (a.aligned && (px % 2)) ? px + 1 : px;
     for (size_t i = 0; i < c.sched.size(); i++) a.sched[i] = c.sched[i];
     double *pH = nullptr, *pg = nullptr, *pll = nullptr;
+    const bool pre = c.pre && family == DLSA_FAMILY_LOGISTIC;
+    const size_t slice_bytes = tiled_slice_bytes(K, S, p);
+    const size_t need = slice_bytes + (pre ? 3 * (size_t)K * (size_t)max_part_rows * sizeof(double) : 0);
+    DLSA_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need), DLSA_E_WORKSPACE,
+                 "irls pass: workspace too small (%zu < %zu)", workspace_bytes, need);
+    a.pre_w = a.pre_r = a.pre_ll = nullptr;
+    if (pre) {
+        double* wbuf = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + slice_bytes);
+        double* rbuf = wbuf + (size_t)K * max_part_rows;
+        double* lbuf = rbuf + (size_t)K * max_part_rows;
+        a.pre_w = wbuf; a.pre_r = rbuf; a.pre_ll = a.want_ll ? lbuf : nullptr;
+        int gx = (int)((max_part_rows + kLinkWarps * 32 - 1) / (kLinkWarps * 32));
+        const int gx_cap = (148 * 8 + K - 1) / K;
+        if (gx > gx_cap) gx = gx_cap;
+        if (gx < 1) gx = 1;
+        const size_t lsm = ((size_t)32 * ((px + 31) / 32) + kLinkWarps * 32) * sizeof(double);
+        tiled_link_kernel<<<dim3(gx, K), kLinkWarps * 32, lsm, st>>>(X, ldx, y, part_off, beta, active, px, a.icpt, wbuf,
+                                                                     rbuf, a.want_ll ? lbuf : nullptr);
+        count_launch();
+        int rc0 = check_launch("tiled_link_kernel");
+        if (rc0) return rc0;
+    }
     if (S == 1) {
         a.outH = H; a.outg = g; a.outll = loglik;
     } else {
-        const size_t need = (size_t)K * S * ((size_t)p * p + p + 1) * sizeof(double);
-        DLSA_REQUIRE(workspace != nullptr && workspace_bytes >= need, DLSA_E_WORKSPACE,
-                     "irls pass: workspace too small (%zu < %zu)", workspace_bytes, need);
         pH = static_cast<double*>(workspace);
         pg = pH + (size_t)K * S * p * p;
         pll = pg + (size_t)K * S * p;
         a.outH = pH; a.outg = pg; a.outll = pll;
     }
     const int grid = K * S * c.TG;
-    if (family == DLSA_FAMILY_LOGISTIC) {
-        auto kern = irls_tiled_kernel<DLSA_FAMILY_LOGISTIC>;
-        DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-        kern<<<grid, kTThreads, c.smem, st>>>(a);
-    } else {
-        auto kern = irls_tiled_kernel<DLSA_FAMILY_LINEAR>;
-        DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-        kern<<<grid, kTThreads, c.smem, st>>>(a);
+#define DLSA_TILED_LAUNCH(FAM_, CH_, PRE_)                                                                        \
+    {                                                                                                             \
+        auto kern = irls_tiled_kernel<FAM_, CH_, PRE_>;                                                           \
+        DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));          \
+        kern<<<grid, kTThreads, c.smem, st>>>(a);                                                                 \
     }
+    if (family == DLSA_FAMILY_LOGISTIC && pre) {
+        if (c.CH == 32) DLSA_TILED_LAUNCH(DLSA_FAMILY_LOGISTIC, 32, true) else DLSA_TILED_LAUNCH(DLSA_FAMILY_LOGISTIC, 16, true)
+    } else if (family == DLSA_FAMILY_LOGISTIC) {
+        if (c.CH == 32) DLSA_TILED_LAUNCH(DLSA_FAMILY_LOGISTIC, 32, false) else DLSA_TILED_LAUNCH(DLSA_FAMILY_LOGISTIC, 16, false)
+    } else {
+        if (c.CH == 32) DLSA_TILED_LAUNCH(DLSA_FAMILY_LINEAR, 32, false) else DLSA_TILED_LAUNCH(DLSA_FAMILY_LINEAR, 16, false)
+    }
+#undef DLSA_TILED_LAUNCH
     count_launch();
     int rc = check_launch("irls_tiled_kernel");
     if (rc) return rc;

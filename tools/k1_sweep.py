@@ -31,8 +31,13 @@ CASES = {
     "p56": (80_000_000, 56, 1024, False, "logistic", 0),
     "p32": (100_000_000, 32, 1024, False, "logistic", 0),
     "c3": (15_000_000, 181, 15, True, "logistic", 1),         # airline-shaped shard of one of 8 GPUs
+    "c3_small": (1_500_000, 181, 15, True, "logistic", 1),
+    "c3_lin": (15_000_000, 182, 15, False, "linear", 1),      # the same Gram without the link stage (ceiling for c3)
+    "c5_lin": (2_560_000, 500, 1024, False, "linear", 1),
     "c4": (50_000_000, 100, 128, False, "linear", 1),         # OLS, p=100 (one GPU's 128 of 1024 partitions)
     "c4_logit": (50_000_000, 100, 128, False, "logistic", 0),
+    "c4_logit_ncu": (10_000_000, 100, 148, False, "logistic", 0),   # the size the tiled-kernel ncu capture uses
+    "c4_ncu": (10_000_000, 100, 148, False, "linear", 1),
     "c5": (2_560_000, 500, 1024, False, "logistic", 0),       # p=500, 2500-row partitions (1024 of 8192)
 }
 
