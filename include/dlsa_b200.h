@@ -69,6 +69,9 @@ unsigned long long dlsa_launch_count(void);
  *   H        [K, p, p]  out: X' diag(prob(1-prob)) X (LINEAR: X'X), full symmetric
  *   loglik   [K]        out: sum y*eta - log(1+exp(eta)) (LINEAR: y'y); NULL to skip computing it
  *   max_part_rows: upper bound of rows in any partition (host int; sizes the grid)
+ *   workspace: partial sums of partitions that are split over several CTAs and, for logistic fits whose Gram triangle
+ *     needs sibling CTAs (p > ~170), w / r / log-likelihood term of every row (24 bytes per row, sized for
+ *     K * max_part_rows rows): there the link stage runs as a streaming kernel of its own ahead of the Gram kernel.
  */
 size_t dlsa_irls_pass_workspace_bytes(int K, int p, int64_t max_part_rows);
 int dlsa_irls_pass_f64(const double *X, int64_t ldx, const double *y, const int64_t *part_off, int K, int px,
