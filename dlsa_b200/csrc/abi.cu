@@ -49,6 +49,9 @@ int loglik_launch(const double*, int64_t, const double*, const int64_t*, int, in
 int onehot_launch(const double*, int, const double*, const double*, const int*, int, const int*, int64_t, double*,
                   int64_t, cudaStream_t);
 
+size_t colstats_workspace_bytes(int px);
+int colstats_launch(const double*, int64_t, int64_t, int, double*, double*, cudaStream_t);
+
 size_t irls_cat_workspace_bytes(int K, int n_cat, const int* n_levels, int64_t max_part_rows);
 int irls_cat_launch(const double*, int64_t, int, const double*, const double*, const int*, int, const int*, const double*,
                     const int64_t*, int, int, const double*, const int*, double*, double*, double*, int64_t, void*,
@@ -195,6 +198,16 @@ int dlsa_onehot_expand_f64(const double* numeric, int n_num, const double* mean,
     DLSA_REQUIRE((n_num == 0 || numeric) && (n_cat == 0 || (codes && col_base)), DLSA_E_BADARG, "onehot: null pointer");
     DLSA_REQUIRE((mean == nullptr) == (std == nullptr), DLSA_E_BADARG, "onehot: mean/std must both be given");
     return onehot_launch(numeric, n_num, mean, std, codes, n_cat, col_base, n, X, ldx, static_cast<cudaStream_t>(stream));
+}
+
+size_t dlsa_column_stats_workspace_bytes(int px) { return px <= 0 ? 0 : colstats_workspace_bytes(px); }
+
+int dlsa_column_stats_f64(const double* X, int64_t ldx, int64_t n, int px, double* stats, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    DLSA_REQUIRE(X && stats && n >= 1 && px >= 1 && ldx >= px, DLSA_E_BADARG, "column stats: bad argument");
+    DLSA_REQUIRE(workspace && workspace_bytes >= colstats_workspace_bytes(px), DLSA_E_WORKSPACE,
+                 "column stats: workspace too small");
+    return colstats_launch(X, ldx, n, px, stats, static_cast<double*>(workspace), static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

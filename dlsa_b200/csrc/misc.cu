@@ -177,4 +177,120 @@ int onehot_launch(const double* numeric, int n_num, const double* mean, const do
     return check_launch("onehot_kernel");
 }
 
+// ---- f-3: describe() — count / mean / sample stddev / min / max of every column in ONE streaming pass -------------
+// Reference: data_info = data_sdf_i.describe().toPandas() (projects/logistic_dlsa.py:279-283), used as
+// (x - mean) / stddev in logistic_model (dlsa/models.py:99-101).  HBM-bound: 8*px bytes per row, read once.
+// Sums are taken about column c's first value (shifted data: no cancellation for columns like Year ~ 2000 +- 5),
+// per CTA in a fixed order, and the CTA partials are merged in a fixed order: bitwise reproducible.
+constexpr int kStatCtas = 148 * 4;
+constexpr int kStatWarps = 8;
+// kStatNS (template): 32-column stripes per sweep — a lane owns columns lane and lane+32 of a sweep (1 stripe for p <= 32)
+constexpr int kStatRU = 4;   // rows in flight per lane and stripe
+// CTA b takes the 32-row tiles b, b + gridDim.x, ... (all CTAs sweep the matrix front together: sequential DRAM
+// streaming); a sweep covers 64 columns, so p <= 64 reads every row once, whole, in one go.
+template <int kStatNS>
+__global__ void __launch_bounds__(kStatWarps * 32, 4) colstats_partial_kernel(const double* __restrict__ X, int64_t ldx,
+                                                                           int64_t n, int px,
+                                                                           double* __restrict__ partial) {
+    __shared__ double red[kStatWarps][32][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kTile = kStatWarps * kStatRU;  // rows per CTA step
+    for (int c0 = 0; c0 < px; c0 += 32 * kStatNS) {
+        double shift[kStatNS], s1[kStatNS], s2[kStatNS], mn[kStatNS], mx[kStatNS];
+        bool in[kStatNS];
+#pragma unroll
+        for (int s = 0; s < kStatNS; s++) {
+            const int c = c0 + 32 * s + lane;
+            in[s] = c < px;
+            shift[s] = in[s] ? __ldg(X + c) : 0.0;
+            s1[s] = s2[s] = 0.0;
+            mn[s] = INFINITY;
+            mx[s] = -INFINITY;
+        }
+        const double* xc = X + c0 + lane;
+        for (int64_t t = blockIdx.x; t * kTile < n; t += gridDim.x) {
+            const int64_t r0 = t * kTile + warp;
+            double v[kStatRU][kStatNS];
+#pragma unroll
+            for (int u = 0; u < kStatRU; u++) {
+                const int64_t r = r0 + (int64_t)u * kStatWarps;
+#pragma unroll
+                for (int s = 0; s < kStatNS; s++)
+                    v[u][s] = (in[s] && r < n) ? __ldg(xc + r * ldx + 32 * s) : shift[s];
+            }
+#pragma unroll
+            for (int u = 0; u < kStatRU; u++) {
+                const bool rv = r0 + (int64_t)u * kStatWarps < n;
+#pragma unroll
+                for (int s = 0; s < kStatNS; s++) {
+                    const double d = v[u][s] - shift[s];  // 0 for rows past the end
+                    s1[s] += d;
+                    s2[s] = fma(d, d, s2[s]);
+                    mn[s] = rv ? fmin(mn[s], v[u][s]) : mn[s];
+                    mx[s] = rv ? fmax(mx[s], v[u][s]) : mx[s];
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < kStatNS; s++) {
+            red[warp][lane][0] = s1[s]; red[warp][lane][1] = s2[s]; red[warp][lane][2] = mn[s]; red[warp][lane][3] = mx[s];
+            __syncthreads();
+            if (warp == 0 && in[s]) {
+                double a1 = 0.0, a2 = 0.0, amn = INFINITY, amx = -INFINITY;
+                for (int w = 0; w < kStatWarps; w++) {
+                    a1 += red[w][lane][0]; a2 += red[w][lane][1];
+                    amn = fmin(amn, red[w][lane][2]); amx = fmax(amx, red[w][lane][3]);
+                }
+                double* o = partial + ((size_t)blockIdx.x * px + c0 + 32 * s + lane) * 4;
+                o[0] = a1; o[1] = a2; o[2] = amn; o[3] = amx;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// stats [5][px]: count, mean, stddev (n-1 denominator, Spark's stddev_samp), min, max.  One warp per column: lane l sums
+// the partials of CTAs l, l+32, ... in order, then a fixed shuffle tree.
+__global__ void __launch_bounds__(128) colstats_final_kernel(const double* __restrict__ partial,
+                                                             const double* __restrict__ X, int ctas, int64_t n, int px,
+                                                             double* __restrict__ stats) {
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= px) return;
+    double s1 = 0.0, s2 = 0.0, mn = INFINITY, mx = -INFINITY;
+    for (int b = lane; b < ctas; b += 32) {
+        const double* o = partial + ((size_t)b * px + c) * 4;
+        s1 += o[0]; s2 += o[1];
+        mn = fmin(mn, o[2]); mx = fmax(mx, o[3]);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        s1 += shfl_xor_f64(s1, m); s2 += shfl_xor_f64(s2, m);
+        mn = fmin(mn, shfl_xor_f64(mn, m)); mx = fmax(mx, shfl_xor_f64(mx, m));
+    }
+    if (lane != 0) return;
+    const double nn = (double)n;
+    const double shift = X[c];
+    const double var = (n > 1) ? fmax(s2 - s1 * s1 / nn, 0.0) / (nn - 1.0) : NAN;
+    stats[c] = nn;
+    stats[px + c] = shift + s1 / nn;
+    stats[2 * px + c] = sqrt(var);
+    stats[3 * px + c] = mn;
+    stats[4 * px + c] = mx;
+}
+
+size_t colstats_workspace_bytes(int px) { return (size_t)kStatCtas * px * 4 * sizeof(double); }
+
+int colstats_launch(const double* X, int64_t ldx, int64_t n, int px, double* stats, double* partial, cudaStream_t st) {
+    int64_t ctas = (n + kStatWarps * kStatRU - 1) / (kStatWarps * kStatRU);
+    if (ctas > kStatCtas) ctas = kStatCtas;
+    if (px <= 32) colstats_partial_kernel<1><<<(int)ctas, kStatWarps * 32, 0, st>>>(X, ldx, n, px, partial);
+    else colstats_partial_kernel<2><<<(int)ctas, kStatWarps * 32, 0, st>>>(X, ldx, n, px, partial);
+    count_launch();
+    int rc = check_launch("colstats_partial_kernel");
+    if (rc) return rc;
+    colstats_final_kernel<<<(px + 3) / 4, 128, 0, st>>>(partial, X, (int)ctas, n, px, stats);
+    count_launch();
+    return check_launch("colstats_final_kernel");
+}
+
 }  // namespace dlsa

@@ -216,3 +216,25 @@ def encode_design_compact(sample_df, Y_name, dummy_info, dummy_factors_baseline,
         std_d = torch.as_tensor(stats[1], device=device)
     return (torch.as_tensor(num, device=device), torch.as_tensor(np.ascontiguousarray(rel), device=device), n_levels,
             (mean_d, std_d), names)
+
+
+def describe(data, columns=None, device=None):
+    """``data_sdf_i.describe().toPandas()`` on the device (projects/logistic_dlsa.py:279-283): a frame with a
+    ``summary`` column (count, mean, stddev, min, max) and one string-valued column per numeric column, so that
+    ``float(data_info[c][1])`` / ``float(data_info[c][2])`` (dlsa/models.py:99-101) read the mean and the sample
+    standard deviation.  ``data``: a pandas frame (its numeric ``columns``) or a float64 CUDA tensor [n, px]."""
+    import pandas as pd
+    from . import engine
+    if isinstance(data, torch.Tensor):
+        X = data
+        names = list(columns) if columns is not None else [f"x{i}" for i in range(X.shape[1])]
+    else:
+        names = list(columns) if columns is not None else [c for c in data.columns
+                                                            if pd.api.types.is_numeric_dtype(data[c])]
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        X = torch.as_tensor(np.ascontiguousarray(data[names].to_numpy(dtype=np.float64)), device=dev)
+    st = engine.column_stats(X).cpu().numpy()
+    out = {"summary": ["count", "mean", "stddev", "min", "max"]}
+    for j, c in enumerate(names):
+        out[c] = [str(int(st[0, j]))] + [repr(float(v)) for v in st[1:, j]]
+    return pd.DataFrame(out)

@@ -451,6 +451,21 @@ def logistic_loglik(X, y, part_offsets, par, fit_intercept=False) -> torch.Tenso
     return out
 
 
+def column_stats(X: torch.Tensor) -> torch.Tensor:
+    """describe() on the device: [5, px] = count, mean, sample stddev, min, max of every column of X [n, px] in one
+    streaming pass (Spark's ``data_sdf_i.describe()``, projects/logistic_dlsa.py:279-283; rows 1 and 2 are what
+    logistic_model standardises with, dlsa/models.py:99-101)."""
+    dev = _require_cuda(X)
+    if X.dtype != _F64 or X.dim() != 2 or X.stride(1) != 1 or X.shape[0] < 1 or X.shape[1] < 1:
+        raise TypeError("X must be a non-empty float64 [n, px] row-major tensor")
+    n, px = X.shape
+    stats = torch.empty(5, px, dtype=_F64, device=dev)
+    ws = _workspace(lib.dlsa_column_stats_workspace_bytes(px), dev)
+    check(lib.dlsa_column_stats_f64(X.data_ptr(), X.stride(0), n, px, stats.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    _stream()), "dlsa_column_stats_f64")
+    return stats
+
+
 def dlsa_fit(X, y, part_offsets, fit_intercept=False, sample_size=None, type="lar", config=None, group=None,
              family="logistic"):
     """Whole hot path on this rank's partitions: map (fit) -> combine (+allreduce) -> LARS + AIC/BIC.

@@ -183,6 +183,14 @@ int dlsa_simulate_f64(double *X, int64_t ldx, double *y, int64_t row0, int64_t n
 int dlsa_onehot_expand_f64(const double *numeric, int n_num, const double *mean, const double *std, const int *codes,
                            int n_cat, const int *col_base, int64_t n, double *X, int64_t ldx, void *stream);
 
+/* f-3  describe(): count, mean, sample standard deviation, min, max of every column of X [n, ldx] in one streaming
+ *   pass — the statistics the reference takes from Spark's data_sdf_i.describe() (projects/logistic_dlsa.py:279-283)
+ *   and applies as (x - mean) / stddev in logistic_model (dlsa/models.py:99-101).
+ *   stats [5, px] out: rows count, mean, stddev (n-1 denominator), min, max.  n >= 1. */
+size_t dlsa_column_stats_workspace_bytes(int px);
+int dlsa_column_stats_f64(const double *X, int64_t ldx, int64_t n, int px, double *stats, void *workspace,
+                          size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,3 +173,40 @@ def test_single_class_partition_raises_like_sklearn():
     df = pd.DataFrame({"partition_id": 0, "label": 1.0, "x0": [1.0, 2.0, 3.0, 4.0], "x1": [0.2, -0.1, 0.3, 0.0]})
     with pytest.raises(ValueError):
         logistic_model(df, "label", config=__import__("dlsa_b200").EngineConfig(max_iter=10))
+
+
+def test_describe_matches_spark_describe_semantics():
+    """projects/logistic_dlsa.py:279-283: data_info = describe() -> rows count/mean/stddev(n-1)/min/max; logistic_model
+    reads rows 1 and 2 (dlsa/models.py:99-101).  Columns with a large mean and a small spread (Year) must not lose
+    digits; standardising with the device statistics must equal standardising with pandas' statistics."""
+    import dlsa_b200
+    from dlsa.utils_spark import describe
+    rng = np.random.default_rng(4)
+    n = 123_457
+    df = pd.DataFrame({"Year": 2000.0 + rng.integers(0, 9, n), "Distance": rng.gamma(2.0, 400.0, n),
+                       "DepTime": rng.integers(0, 2400, n).astype(float), "z": rng.standard_normal(n) * 1e-3 + 7e5,
+                       "const": np.full(n, 3.25), "Carrier": rng.choice(list("ABC"), n)})
+    info = describe(df)
+    assert list(info["summary"]) == ["count", "mean", "stddev", "min", "max"]
+    num = ["Year", "Distance", "DepTime", "z", "const"]
+    assert list(info.columns) == ["summary"] + num           # non-numeric columns are left out
+    ref = df[num].describe()
+    for c in num:
+        assert int(info[c][0]) == n
+        assert abs(float(info[c][1]) - ref[c]["mean"]) <= 1e-12 * abs(ref[c]["mean"])
+        assert abs(float(info[c][2]) - ref[c]["std"]) <= 1e-10 * ref[c]["std"] + 1e-300
+        assert float(info[c][3]) == ref[c]["min"] and float(info[c][4]) == ref[c]["max"]
+    # tensor entry, wide and ragged shapes, run-to-run reproducible
+    for px in (1, 31, 50, 182):
+        X = torch.as_tensor(rng.standard_normal((5003, px)) * 3 + 10, device="cuda")
+        st = dlsa_b200.column_stats(X)
+        assert torch.equal(st, dlsa_b200.column_stats(X))
+        Xh = X.cpu().numpy()
+        assert np.allclose(st[1].cpu().numpy(), Xh.mean(0), rtol=1e-13)
+        assert np.allclose(st[2].cpu().numpy(), Xh.std(0, ddof=1), rtol=1e-12)
+        assert np.array_equal(st[3].cpu().numpy(), Xh.min(0)) and np.array_equal(st[4].cpu().numpy(), Xh.max(0))
+    # strided view (ldx > px) and a single row
+    Xs = torch.as_tensor(rng.standard_normal((777, 12)), device="cuda")[:, :7]
+    assert np.allclose(dlsa_b200.column_stats(Xs)[1].cpu().numpy(), Xs.cpu().numpy().mean(0), rtol=1e-12, atol=1e-15)
+    one = dlsa_b200.column_stats(torch.ones(1, 3, dtype=torch.float64, device="cuda"))
+    assert one[0].tolist() == [1.0, 1.0, 1.0] and torch.isnan(one[2]).all()  # Spark: stddev of one row is NaN/null

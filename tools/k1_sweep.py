@@ -116,6 +116,32 @@ def main():
     hbm, f64 = peaks()
     lines = []
     for name in args.cases.split(","):
+        if name.startswith("describe"):  # the column-statistics pass (HBM-bound): describe_<px>
+            px = int(name.split("_")[1]) if "_" in name else 50
+            n = 4_000_000_000 // (8 * px)
+            X = torch.empty(n, px, dtype=torch.float64, device=dev)
+            synth.simulate_logistic_device(min(n, 5_000_000), px, 7, dev, out=(X[:min(n, 5_000_000)], torch.empty(min(n, 5_000_000), dtype=torch.float64, device=dev)))
+            X[5_000_000:] = 0.25
+            for _ in range(2):
+                engine.column_stats(X)
+            torch.cuda.synchronize()
+            times = []
+            for _ in range(args.reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                engine.column_stats(X)
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+            ms = sorted(times)[len(times) // 2]
+            gbs = n * px * 8 / (ms * 1e-3) / 1e9
+            line = {"case": name, "kernel": "colstats_partial_kernel (describe)", "rows": n, "px": px, "ms": round(ms, 4),
+                    "GBps": round(gbs, 1), "hbm_frac": round(gbs / hbm, 4)}
+            print(json.dumps(line), flush=True)
+            lines.append(line)
+            del X
+            torch.cuda.empty_cache()
+            continue
         if name in CAT_CASES:
             line = run_cat(name, args.reps, hbm)
             print(json.dumps(line), flush=True)
