@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libdlsa_b200.so")
 
 ABI_VERSION = 1
 ST_OK, ST_NOT_CONVERGED, ST_NOT_SPD, ST_SKIPPED = 0, 1, 2, 4
-FAMILY_LOGISTIC, FAMILY_LINEAR = 0, 1
+FAMILY_LOGISTIC, FAMILY_LINEAR, FAMILY_POISSON = 0, 1, 2
 LARS_LAR, LARS_LASSO = 0, 1
 
 

@@ -80,7 +80,7 @@ int dlsa_irls_pass_f64(const double* X, int64_t ldx, const double* y, const int6
                        double* loglik, int64_t max_part_rows, void* workspace, size_t workspace_bytes, void* stream) {
     DLSA_REQUIRE(K >= 0 && px >= 1 && ldx >= px, DLSA_E_BADARG, "irls pass: bad shape K=%d px=%d ldx=%lld", K, px,
                  (long long)ldx);
-    DLSA_REQUIRE(family == DLSA_FAMILY_LOGISTIC || family == DLSA_FAMILY_LINEAR, DLSA_E_BADARG,
+    DLSA_REQUIRE(family == DLSA_FAMILY_LOGISTIC || family == DLSA_FAMILY_LINEAR || family == DLSA_FAMILY_POISSON, DLSA_E_BADARG,
                  "irls pass: unknown family %d", family);
     DLSA_REQUIRE(X && y && part_off && g && H, DLSA_E_BADARG, "irls pass: null pointer");
     DLSA_REQUIRE(family == DLSA_FAMILY_LINEAR || beta != nullptr, DLSA_E_BADARG, "irls pass: beta is null");

@@ -96,9 +96,12 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int m) { return __shfl_
 // code: CUDA's exp() and '/' carry slow-path branches/calls that split the basic block.  These versions are
 // branch-free and accurate to ~1 ulp on the ranges used here.
 
-// exp(x) for x <= 0 (argument clamped at -708: below that 1 + exp(x) == 1 anyway).
-__device__ __forceinline__ double exp_nonpos(double x) {
-    x = fmax(x, -708.0);
+// exp(x) for x in [-708, 709] (clamped: below -708, 1 + exp(x) == 1 anyway; 709 is the last finite exp), branch-free.
+// exp_nonpos is the same routine under its historical name: the logistic link only calls it with x <= 0.
+__device__ __forceinline__ double exp_clamped(double x);
+__device__ __forceinline__ double exp_nonpos(double x) { return exp_clamped(x); }
+__device__ __forceinline__ double exp_clamped(double x) {
+    x = fmin(fmax(x, -708.0), 709.0);
     const double kShift = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
     const double t = fma(x, 1.4426950408889634074, kShift);
     const int n = __double2loint(t);
@@ -119,7 +122,7 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    return p * __hiloint2double((n + 1023) << 20, 0);    // * 2^n, n in [-1022, 0]
+    return p * __hiloint2double((n + 1023) << 20, 0);    // * 2^n, n in [-1022, 1023]
 }
 
 // num / den for a positive normal den of moderate size: MUFU.RCP64H seed, two Newton steps, one residual

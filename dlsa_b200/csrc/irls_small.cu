@@ -32,6 +32,7 @@ struct IrlsArgs {
     double* outg;   // [K*S][p]
     double* outll;  // [K*S] or nullptr
     int K, px, p, icpt, S, aligned, want_ll;
+    int poisson;  // GLM instantiation only: 0 = logistic link, 1 = log link (DLSA_FAMILY_POISSON)
 };
 
 constexpr int kMmaWarps = 8;
@@ -218,10 +219,17 @@ __global__ void __launch_bounds__(kThreads, 1) irls_small_kernel(const IrlsArgs 
                             s[g] += shfl_xor_f64(s[g], 2);
                             eta = (q == g) ? s[g] : eta;
                         }
-                        const double pr = sigmoid_f64(eta);
-                        wv = pr * (1.0 - pr);
-                        rv = y_cur[u] - pr;
-                        if (a.want_ll && rowvalid) llacc += y_cur[u] * eta - log1pexp_f64(eta);
+                        if (a.poisson) {  // warp-uniform: mu = exp(eta), w = mu, r = y - mu (dlsa/R/wlse_func.R:155-168)
+                            const double mu = exp_clamped(eta);
+                            wv = mu;
+                            rv = y_cur[u] - mu;
+                            if (a.want_ll && rowvalid) llacc += fma(y_cur[u], eta, -mu);
+                        } else {
+                            const double pr = sigmoid_f64(eta);
+                            wv = pr * (1.0 - pr);
+                            rv = y_cur[u] - pr;
+                            if (a.want_ll && rowvalid) llacc += y_cur[u] * eta - log1pexp_f64(eta);
+                        }
                     } else {
                         wv = 1.0;
                         rv = y_cur[u];
@@ -459,7 +467,7 @@ int irls_small_slices(int K, int p, int64_t max_part_rows) {
 
 template <int NT, int REM, int CH, int STAGES>
 static int launch_cfg(const IrlsArgs& a, int family, size_t smem, int grid, cudaStream_t st) {
-    if (family == DLSA_FAMILY_LOGISTIC) {
+    if (family != DLSA_FAMILY_LINEAR) {
         auto kern = irls_small_kernel<NT, REM, CH, STAGES, DLSA_FAMILY_LOGISTIC>;
         DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kThreads, smem, st>>>(a);
@@ -499,6 +507,7 @@ int irls_small_launch(const double* X, int64_t ldx, const double* y, const int64
     // TMA staging copies GR consecutive rows with one bulk copy: rows must be contiguous (ldx == px), 16-byte aligned
     a.aligned = ((reinterpret_cast<uintptr_t>(X) & 15) == 0 && ldx == px && (px % 2) == 0) ? 1 : 0;
     a.want_ll = loglik != nullptr;
+    a.poisson = family == DLSA_FAMILY_POISSON ? 1 : 0;
     double *pH = nullptr, *pg = nullptr, *pll = nullptr;
     if (S == 1) {
         a.outH = H; a.outg = g; a.outll = loglik;

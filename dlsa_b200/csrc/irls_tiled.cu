@@ -70,6 +70,7 @@ struct TiledArgs {
     const double* pre_r;   // tiled_link_kernel, indexed by global row
     const double* pre_ll;
     int K, px, p, icpt, S, Sd, aligned, want_ll, NT, TG, stages, copy_cols;
+    int poisson;  // GLM instantiation only: 0 = logistic link, 1 = log link (DLSA_FAMILY_POISSON)
     // block of MMA warp w, slot b of sibling tg: bits 0-7 valid-tile mask (bit 4*ii+jj), 8-15 row pair m, 16-23 column
     // group J, 24 g-owner flag, 25-27 partial pattern; 0 = empty slot.  Full blocks first, the partial one last.
     uint32_t sched[kTMaxTG * kTMma * kTNBW];
@@ -282,11 +283,18 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
                 double eta = (a0 + a1) + (a2 + a3);
                 if (kTCH == 16) eta += shfl_xor_f64(eta, 16);
                 eta += b0;
-                const double e = exp_nonpos(-fabs(eta));
-                const double pr = div_pos((eta >= 0.0) ? 1.0 : e, 1.0 + e);
-                wv = pr * (1.0 - pr);
-                rv = yv - pr;
-                if (a.want_ll && rowvalid) llacc += yv * eta - (fmax(eta, 0.0) + log1p_01(e));
+                if (a.poisson) {  // warp-uniform: mu = exp(eta), w = mu, r = y - mu (dlsa/R/wlse_func.R:155-168)
+                    const double mu = exp_clamped(eta);
+                    wv = mu;
+                    rv = yv - mu;
+                    if (a.want_ll && rowvalid) llacc += fma(yv, eta, -mu);
+                } else {
+                    const double e = exp_nonpos(-fabs(eta));
+                    const double pr = div_pos((eta >= 0.0) ? 1.0 : e, 1.0 + e);
+                    wv = pr * (1.0 - pr);
+                    rv = yv - pr;
+                    if (a.want_ll && rowvalid) llacc += yv * eta - (fmax(eta, 0.0) + log1p_01(e));
+                }
             } else {
                 mbar_wait(smem_u32(&bars[st * 4 + 0]), par);  // the stage belongs to this chunk now
                 wv = 1.0;
@@ -440,8 +448,8 @@ __global__ void __launch_bounds__(kLinkWarps * 32) tiled_link_kernel(const doubl
                                                                      const int64_t* __restrict__ part_off,
                                                                      const double* __restrict__ beta,
                                                                      const int* __restrict__ active, int px, int icpt,
-                                                                     double* __restrict__ wout, double* __restrict__ rout,
-                                                                     double* __restrict__ llout) {
+                                                                     int poisson, double* __restrict__ wout,
+                                                                     double* __restrict__ rout, double* __restrict__ llout) {
     extern __shared__ double link_s[];  // beta [32 * jn] | eta [kLinkWarps][32]
     const int k = blockIdx.y;
     if (active != nullptr && active[k] == 0) return;
@@ -494,11 +502,18 @@ __global__ void __launch_bounds__(kLinkWarps * 32) tiled_link_kernel(const doubl
         if (r < n_k) {
             const double eta = eta_s[warp * 32 + lane] + b0;
             const double yv = __ldg(y + row_lo + r);
-            const double e = exp_nonpos(-fabs(eta));
-            const double pr = div_pos((eta >= 0.0) ? 1.0 : e, 1.0 + e);
-            wout[row_lo + r] = pr * (1.0 - pr);
-            rout[row_lo + r] = yv - pr;
-            if (llout != nullptr) llout[row_lo + r] = yv * eta - (fmax(eta, 0.0) + log1p_01(e));
+            if (poisson) {
+                const double mu = exp_clamped(eta);
+                wout[row_lo + r] = mu;
+                rout[row_lo + r] = yv - mu;
+                if (llout != nullptr) llout[row_lo + r] = fma(yv, eta, -mu);
+            } else {
+                const double e = exp_nonpos(-fabs(eta));
+                const double pr = div_pos((eta >= 0.0) ? 1.0 : e, 1.0 + e);
+                wout[row_lo + r] = pr * (1.0 - pr);
+                rout[row_lo + r] = yv - pr;
+                if (llout != nullptr) llout[row_lo + r] = yv * eta - (fmax(eta, 0.0) + log1p_01(e));
+            }
         }
         __syncwarp();
     }
@@ -686,7 +701,9 @@ int irls_tiled_launch(const double* X, int64_t ldx, const double* y, const int64
     a.copy_cols = (a.aligned && (px % 2)) ? px + 1 : px;
     for (size_t i = 0; i < c.sched.size(); i++) a.sched[i] = c.sched[i];
     double *pH = nullptr, *pg = nullptr, *pll = nullptr;
-    const bool pre = c.pre && family == DLSA_FAMILY_LOGISTIC;
+    const bool glm = family != DLSA_FAMILY_LINEAR;  // logistic or Poisson: the GLM instantiation, link chosen at run time
+    a.poisson = family == DLSA_FAMILY_POISSON ? 1 : 0;
+    const bool pre = c.pre && glm;
     const size_t slice_bytes = tiled_slice_bytes(K, S, p);
     const size_t need = slice_bytes + (pre ? 3 * (size_t)K * (size_t)max_part_rows * sizeof(double) : 0);
     DLSA_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need), DLSA_E_WORKSPACE,
@@ -702,8 +719,8 @@ int irls_tiled_launch(const double* X, int64_t ldx, const double* y, const int64
         if (gx > gx_cap) gx = gx_cap;
         if (gx < 1) gx = 1;
         const size_t lsm = ((size_t)32 * ((px + 31) / 32) + kLinkWarps * 32) * sizeof(double);
-        tiled_link_kernel<<<dim3(gx, K), kLinkWarps * 32, lsm, st>>>(X, ldx, y, part_off, beta, active, px, a.icpt, wbuf,
-                                                                     rbuf, a.want_ll ? lbuf : nullptr);
+        tiled_link_kernel<<<dim3(gx, K), kLinkWarps * 32, lsm, st>>>(X, ldx, y, part_off, beta, active, px, a.icpt,
+                                                                     a.poisson, wbuf, rbuf, a.want_ll ? lbuf : nullptr);
         count_launch();
         int rc0 = check_launch("tiled_link_kernel");
         if (rc0) return rc0;
@@ -723,9 +740,9 @@ int irls_tiled_launch(const double* X, int64_t ldx, const double* y, const int64
         DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));          \
         kern<<<grid, kTThreads, c.smem, st>>>(a);                                                                 \
     }
-    if (family == DLSA_FAMILY_LOGISTIC && pre) {
+    if (glm && pre) {
         if (c.CH == 32) DLSA_TILED_LAUNCH(DLSA_FAMILY_LOGISTIC, 32, true) else DLSA_TILED_LAUNCH(DLSA_FAMILY_LOGISTIC, 16, true)
-    } else if (family == DLSA_FAMILY_LOGISTIC) {
+    } else if (glm) {
         if (c.CH == 32) DLSA_TILED_LAUNCH(DLSA_FAMILY_LOGISTIC, 32, false) else DLSA_TILED_LAUNCH(DLSA_FAMILY_LOGISTIC, 16, false)
     } else {
         if (c.CH == 32) DLSA_TILED_LAUNCH(DLSA_FAMILY_LINEAR, 32, false) else DLSA_TILED_LAUNCH(DLSA_FAMILY_LINEAR, 16, false)

@@ -234,7 +234,8 @@ def _fit_warm(make_pass, part_offsets, K: int, p: int, dev, cfg: EngineConfig, n
 
 def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor, fit_intercept: bool = False,
                             config: Optional[EngineConfig] = None, beta_init: Optional[torch.Tensor] = None,
-                            pooled_start: Optional[torch.Tensor] = None) -> PartitionFits:
+                            pooled_start: Optional[torch.Tensor] = None, family: int = _lib.FAMILY_LOGISTIC
+                            ) -> PartitionFits:
     """Per-partition logistic MLE for every partition at once (the map side, dlsa/models.py:42-147).
 
     X [n, px] float64 row-major on the GPU with each partition's rows contiguous; ``part_offsets`` int64 [K+1].
@@ -254,11 +255,21 @@ def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torc
         ws_pass = _workspace(lib.dlsa_irls_pass_workspace_bytes(offsets.numel() - 1, p, max_rows), dev)
 
         def pass_fn(beta, active, out, want_ll, full):
-            irls_pass(X, y, offsets, beta, fit_intercept, _lib.FAMILY_LOGISTIC, active, max_rows,
+            irls_pass(X, y, offsets, beta, fit_intercept, family, active, max_rows,
                       want_loglik=want_ll, out=out, workspace=ws_pass, full=full)
         return pass_fn
 
     return _fit_warm(make_pass, part_offsets, K, p, dev, cfg, int(X.shape[0]), beta_init, pooled_start)
+
+
+def fit_poisson_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor, fit_intercept: bool = False,
+                           config: Optional[EngineConfig] = None, beta_init: Optional[torch.Tensor] = None
+                           ) -> PartitionFits:
+    """Per-partition Poisson (log-link) MLE: R ``glm(y ~ x - 1, family = "poisson")`` + ``solve(vcov)`` per block
+    (dlsa/R/wlse_func.R:155-168).  Same Newton loop and kernels as the logistic map with the link stage switched:
+    mu = exp(eta), g = X'(y - mu), Sig_inv = X' diag(mu) X at the returned coefficients (IRLS with the canonical link
+    is exactly this Newton iteration; R starts it from mustart = y + 0.1, here from 0 or the pooled warm start)."""
+    return fit_logistic_partitions(X, y, part_offsets, fit_intercept, config, beta_init, None, _lib.FAMILY_POISSON)
 
 
 def _check_cat_inputs(numeric, codes, n_levels, y, part_offsets):
@@ -474,8 +485,10 @@ def dlsa_fit(X, y, part_offsets, fit_intercept=False, sample_size=None, type="la
         fits = fit_logistic_partitions(X, y, part_offsets, fit_intercept, config)
     elif family == "linear":
         fits = fit_linear_partitions(X, y, part_offsets)
+    elif family == "poisson":
+        fits = fit_poisson_partitions(X, y, part_offsets, fit_intercept, config)
     else:
-        raise ValueError("family must be 'logistic' or 'linear'")
+        raise ValueError("family must be 'logistic', 'linear' or 'poisson'")
     comb = combine_partitions(fits, group=group)
     if sample_size is None:
         n = torch.tensor([float(X.shape[0])], dtype=_F64, device=X.device)

@@ -166,3 +166,16 @@ def linear_model(sample_df, Y_name, dummy_factors_baseline=[]):
     if int(fits.status.item()) != 0:
         raise ValueError("linear_model: X'X is not positive definite")
     return _frame(fits.coef[0].cpu().numpy(), fits.Sig_invMcoef[0].cpu().numpy(), fits.Sig_inv[0].cpu().numpy(), names)
+
+
+def poisson_model(sample_df, Y_name, fit_intercept=False, dummy_factors_baseline=[], config=None):
+    """Poisson (log link) regression on one partition in the frame layout of ``logistic_model``: coef = the MLE of
+    R ``glm(y ~ x - 1, family = "poisson")``, Sig_inv = solve(vcov) = X' diag(mu) X (dlsa/R/wlse_func.R:155-168)."""
+    sample_df = sample_df.reset_index(drop=True)
+    X, y, names = _design(sample_df, Y_name, fit_intercept, [], dummy_factors_baseline, [])
+    off = torch.tensor([0, X.shape[0]], dtype=torch.int64, device=X.device)
+    fits = engine.fit_poisson_partitions(X, y, off, fit_intercept=fit_intercept, config=config)
+    if int(fits.status.item()) != 0:
+        raise ValueError("poisson_model: the Newton iteration did not converge")
+    return _frame(fits.coef[0].cpu().numpy(), fits.Sig_invMcoef[0].cpu().numpy(), fits.Sig_inv[0].cpu().numpy(),
+                  (["intercept"] if fit_intercept else []) + names)

@@ -40,6 +40,7 @@ extern "C" {
 /* model family of the fused pass */
 #define DLSA_FAMILY_LOGISTIC 0
 #define DLSA_FAMILY_LINEAR 1
+#define DLSA_FAMILY_POISSON 2  /* log link: mu = exp(eta), w = mu, r = y - mu (R glm(family = "poisson"), dlsa/R/wlse_func.R:155-168) */
 
 /* LARS path type (dlsa/lsa.py:90 `type`) */
 #define DLSA_LARS_LAR 0
@@ -58,6 +59,8 @@ unsigned long long dlsa_launch_count(void);
  *   predict_proba + Sig_inv = X' diag(p(1-p)) X                          dlsa/models.py:114,130
  *   R logistic(): grad = colSums((Y-prob)*X), hess = t(X)%*%(prob*(1-prob)*X)   dlsa/R/wlse_func.R:52-54
  * family = LINEAR gives X'X, X'y, y'y instead (R lm per block, dlsa/R/wlse_func.R:169-182).
+ * family = POISSON: prob -> mu = exp(eta): g = X'(y - mu), H = X' diag(mu) X (= solve(vcov(glm(y~x-1, poisson))),
+ *   dlsa/R/wlse_func.R:155-168), loglik = sum y*eta - mu (without the -log(y!) constant).
  *
  *   X        [n, ldx] float64 row-major, px feature columns used (px <= ldx)
  *   y        [n] float64 labels (0/1) or responses

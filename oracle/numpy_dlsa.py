@@ -93,6 +93,35 @@ def logistic_newton(X, y, tol=1e-10, max_iter=50, damp=True):
     return beta, max_iter
 
 
+def poisson_pass(X, y, beta):
+    """One Newton pass of the Poisson log-link GLM — what R's glm.fit iterates for family = "poisson"
+    (dlsa/R/wlse_func.R:155-168): mu = exp(X beta), g = X'(y - mu), H = X' diag(mu) X (= solve(vcov) at the MLE),
+    loglik = sum y*eta - mu (the -log(y!) constant is dropped)."""
+    eta = X @ beta
+    mu = np.exp(eta)
+    return X.T @ (y - mu), (X * mu[:, None]).T @ X, float(np.sum(y * eta - mu))
+
+
+def poisson_fit(X, y, fit_intercept=False, tol=1e-10, max_iter=50):
+    """MLE of glm(y ~ x - 1, family = "poisson") by exact Newton from beta = 0 with the step rule of the logistic fitter
+    (delta*0.01 when max|delta| > 5, stop on max|delta| <= tol); returns (coef, Sig_inv = X'diag(mu)X, Sig_inv coef)."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).ravel()
+    if fit_intercept:
+        X = np.concatenate([np.ones((X.shape[0], 1)), X], axis=1)
+    beta = np.zeros(X.shape[1])
+    for _ in range(max_iter):
+        g, H, _ = poisson_pass(X, y, beta)
+        delta = np.linalg.solve(H, g)
+        if np.max(np.abs(delta)) > 5:
+            delta = delta * 0.01
+        if np.max(np.abs(delta)) <= tol:
+            break
+        beta = beta + delta
+    _, H, _ = poisson_pass(X, y, beta)
+    return beta, H, H @ beta
+
+
 def logistic_fit(X, y, fit_intercept=False, tol=1e-10, max_iter=50):
     """dlsa/models.py:110-131 with the fit done by exact Newton: returns (coef[p], Sig_inv[p,p],
     Sig_invMcoef[p]); with an intercept the design is [1, X] and the intercept comes first (:116-122).

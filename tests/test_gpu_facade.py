@@ -210,3 +210,20 @@ def test_describe_matches_spark_describe_semantics():
     assert np.allclose(dlsa_b200.column_stats(Xs)[1].cpu().numpy(), Xs.cpu().numpy().mean(0), rtol=1e-12, atol=1e-15)
     one = dlsa_b200.column_stats(torch.ones(1, 3, dtype=torch.float64, device="cuda"))
     assert one[0].tolist() == [1.0, 1.0, 1.0] and torch.isnan(one[2]).all()  # Spark: stddev of one row is NaN/null
+
+
+def test_poisson_model_frame():
+    """models.poisson_model: the frame layout of logistic_model with the estimates of R's glm(family="poisson")."""
+    from dlsa.models import poisson_model
+    rng = np.random.default_rng(12)
+    n, p = 4000, 5
+    X = rng.random((n, p)) - 0.5
+    y = rng.poisson(np.exp(X @ np.array([1.0, -1.0, 0.5, 0.0, 0.0]) + 0.3)).astype(np.float64)
+    df = pd.DataFrame(X, columns=[f"x{i}" for i in range(p)])
+    df.insert(0, "label", y)
+    df.insert(0, "partition_id", 0)
+    out = poisson_model(df, "label", fit_intercept=True)
+    c0, S0, Sc0 = onp.poisson_fit(X, y, fit_intercept=True)
+    assert list(out.columns) == ["par_id", "coef", "Sig_invMcoef", "intercept"] + [f"x{i}" for i in range(p)]
+    assert np.max(np.abs(out["coef"].to_numpy() - c0)) < 1e-9
+    assert np.linalg.norm(out.iloc[:, 3:].to_numpy() - S0) / np.linalg.norm(S0) < 1e-9

@@ -415,3 +415,57 @@ def test_host_entry_pipelined_blocks_match_device_entry(eng):
         assert p1.argmin_BIC == p0.argmin_BIC and torch.equal(p1.beta != 0, p0.beta != 0)
     with pytest.raises(ValueError):
         eng.dlsa_fit_host(dev(X), yh, offh)
+
+
+@pytest.mark.parametrize("px,icpt", [(9, True), (50, False), (100, False), (181, True)])
+def test_poisson_pass_and_fit_match_oracle(eng, px, icpt):
+    """DLSA_FAMILY_POISSON (R glm(y~x-1, family="poisson") per block, dlsa/R/wlse_func.R:155-168) through the small
+    kernel (p <= 56), the tiled kernel with fused link warps (p = 100) and with the streaming link kernel (p = 182)."""
+    from dlsa_b200 import _lib
+    rng = np.random.default_rng(100 + px)
+    sizes = [3000, 1, 2047]
+    off = ragged_offsets(sizes)
+    n, p = int(off[-1]), px + int(icpt)
+    X = rng.random((n, px)) - 0.5
+    truth = np.r_[np.ones(min(8, px)), np.zeros(px - min(8, px))] * (0.5 if px > 60 else 1.0)
+    y = rng.poisson(np.exp(X @ truth + (0.4 if icpt else 0.0))).astype(np.float64)
+    beta = rng.standard_normal((len(sizes), p)) * (1.0 / np.sqrt(p))
+    Xd, yd, od = dev(X), dev(y), dev(off, torch.int64)
+    g, H, ll = eng.irls_pass(Xd, yd, od, dev(beta), fit_intercept=icpt, family=_lib.FAMILY_POISSON)
+    for k, nk in enumerate(sizes):
+        Xk = X[off[k]:off[k + 1]]
+        if icpt:
+            Xk = np.concatenate([np.ones((nk, 1)), Xk], axis=1)
+        g0, H0, ll0 = onp.poisson_pass(Xk, y[off[k]:off[k + 1]], beta[k])
+        assert np.allclose(g[k].cpu().numpy(), g0, rtol=1e-10, atol=1e-9), k
+        assert relfro(H[k].cpu().numpy(), H0) < 1e-12, k
+        assert abs(ll[k].item() - ll0) <= 1e-11 * max(1.0, abs(ll0))
+    fits = eng.fit_poisson_partitions(Xd, yd, dev(ragged_offsets([3000, 2048]), torch.int64), fit_intercept=icpt)
+    assert int(fits.status.abs().sum().item()) == 0
+    for k, (lo, hi) in enumerate([(0, 3000), (3000, 5048)]):
+        c0, S0, Sc0 = onp.poisson_fit(X[lo:hi], y[lo:hi], fit_intercept=icpt)
+        assert np.max(np.abs(fits.coef[k].cpu().numpy() - c0)) < 1e-9
+        assert relfro(fits.Sig_inv[k].cpu().numpy(), S0) < SIG_RTOL
+        assert np.allclose(fits.Sig_invMcoef[k].cpu().numpy(), Sc0, rtol=1e-8, atol=1e-8)
+
+
+def test_poisson_dlsa_end_to_end(eng):
+    """Poisson DLSA: per-partition glm fits -> one-round combine -> LARS + BIC, against the oracle; the pooled warm
+    start (K >= 64) must give the cold-start estimates."""
+    rng = np.random.default_rng(8)
+    K, nk, p = 64, 1500, 12
+    n = K * nk
+    X = rng.random((n, p)) - 0.5
+    truth = np.r_[np.ones(4), np.zeros(p - 4)]
+    y = rng.poisson(np.exp(X @ truth)).astype(np.float64)
+    off = np.arange(K + 1, dtype=np.int64) * nk
+    fits, comb, path = eng.dlsa_fit(dev(X), dev(y), dev(off, torch.int64), sample_size=n, family="poisson")
+    assert int(fits.status.abs().sum().item()) == 0 and fits.pilot_partitions == 8
+    ref = [onp.poisson_fit(X[off[k]:off[k + 1]], y[off[k]:off[k + 1]]) for k in range(K)]
+    th, one, S = onp.combine(np.stack([r[0] for r in ref]), np.stack([r[1] for r in ref]))
+    assert np.max(np.abs(comb.beta_byOLS.cpu().numpy() - th)) < THETA_TOL
+    assert relfro(comb.Sig_inv_sum.cpu().numpy(), S) < SIG_RTOL
+    rp = onp.lars_lsa(S, th, False, n)
+    assert np.array_equal(path.beta.cpu().numpy() != 0, rp["beta"] != 0)
+    assert path.argmin_BIC == int(np.argmin(rp["BIC"]))
+    assert np.array_equal(path.beta[path.argmin_BIC].cpu().numpy() != 0, truth != 0)

@@ -202,3 +202,25 @@ def test_oracle_against_live_reference():
         r = ref_shim.ref_lars_lsa(S, theta, False, 9000, type=typ)
         f = onp.lars_lsa(S, theta, False, 9000, type=typ)
         assert np.max(np.abs(r["beta"] - f["beta"])) < 1e-9
+
+
+def test_poisson_oracle_against_sklearn_glm():
+    """R's glm(y ~ x - 1, family = "poisson") (dlsa/R/wlse_func.R:155-168) cannot run here (no R): the oracle's Poisson
+    Newton is cross-checked against scikit-learn's PoissonRegressor (unpenalised: the same MLE) and against the score
+    equation.  Parity of the Poisson family is therefore UNPINNED with respect to the reference's own R output."""
+    from sklearn.linear_model import PoissonRegressor
+    rng = np.random.default_rng(17)
+    n, p = 8000, 9
+    X = rng.random((n, p)) - 0.5
+    beta = np.r_[np.ones(4), np.zeros(p - 4)]
+    for icpt in (False, True):
+        eta = X @ beta + (0.7 if icpt else 0.0)
+        y = rng.poisson(np.exp(eta)).astype(np.float64)
+        coef, Sig, Sc = onp.poisson_fit(X, y, fit_intercept=icpt)
+        Xd = np.concatenate([np.ones((n, 1)), X], axis=1) if icpt else X
+        g, H, ll = onp.poisson_pass(Xd, y, coef)
+        assert np.max(np.abs(np.linalg.solve(H, g))) < 1e-10          # score equation
+        assert np.array_equal(Sig, H) and np.allclose(Sc, H @ coef)
+        sk = PoissonRegressor(alpha=0.0, fit_intercept=icpt, tol=1e-12, max_iter=2000, solver="newton-cholesky").fit(X, y)
+        ref = np.r_[sk.intercept_, sk.coef_] if icpt else sk.coef_
+        assert np.max(np.abs(coef - ref)) < 1e-7
