@@ -40,6 +40,7 @@ class EngineConfig:
     warm_min_partitions: int = 64
     pilot_fraction: float = 1.0 / 32.0
     pilot_min: int = 8
+    pilot_tol: float = 1e-3     # the pilot only supplies a starting point: it stops at max|delta| <= max(tol, pilot_tol)
 
 
 @dataclasses.dataclass
@@ -163,19 +164,35 @@ def _newton_fit(pass_fn, K: int, p: int, dev, cfg: EngineConfig, n_rows: int, be
     n_active = torch.zeros(1, dtype=torch.int32, device=dev)
     max_delta = torch.zeros(K, dtype=_F64, device=dev)
     ws_chol = _workspace(lib.dlsa_newton_update_workspace_bytes(K, p), dev)
-    passes = 0
-    left = K
-    for _ in range(cfg.max_iter):
-        pass_fn(beta, active, (g, H, None), False, whole_batch and left == K)
-        passes += 1
+    # The host learns "how many partitions are still active" one iteration late: the count goes to pinned memory with an
+    # asynchronous copy and is read only after the NEXT pass has been queued, so the GPU never idles on the host's
+    # round trip.  The pass queued after the last partition converged finds every partition inactive and exits at once.
+    flags = torch.empty(max(cfg.max_iter, 1), dtype=torch.int32).pin_memory()
+    events = []
+    done_at = None
+    for it in range(cfg.max_iter):
+        pass_fn(beta, active, (g, H, None), False, whole_batch and it == 0)
         n_active.zero_()
         check(lib.dlsa_newton_update_f64(H.data_ptr(), g.data_ptr(), K, p, beta.data_ptr(), max_delta.data_ptr(),
                                          status.data_ptr(), active.data_ptr(), iters.data_ptr(), n_active.data_ptr(),
                                          cfg.tol, cfg.damp_above, cfg.damp_factor, ws_chol.data_ptr(),
                                          ws_chol.numel(), _stream()), "dlsa_newton_update_f64")
-        left = int(n_active.item())  # the one host read per iteration
-        if left == 0:
-            break
+        flags[it:it + 1].copy_(n_active, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        events.append(ev)
+        if it >= 1:
+            events[it - 1].synchronize()
+            if int(flags[it - 1]) == 0:
+                done_at = it - 1
+                break
+    if done_at is None and events:
+        events[-1].synchronize()
+        left = int(flags[len(events) - 1])
+        passes = len(events)
+    else:
+        left = 0
+        passes = (done_at + 1) if done_at is not None else 0
     # A converged partition's last step (max|delta| <= tol) is not applied by K2, so its H is already Sig_inv at the
     # returned coefficients (dlsa/models.py:114,130): no extra pass.  Only partitions that ran out of iterations get
     # one more pass at the coefficients they return.
@@ -213,7 +230,7 @@ def _fit_warm(make_pass, part_offsets, K: int, p: int, dev, cfg: EngineConfig, n
         warm = True
     elif beta_init is None and cfg.warm_start and K >= max(2, cfg.warm_min_partitions):
         Kp = min(K, max(int(cfg.pilot_min), int(K * cfg.pilot_fraction)))
-        pcfg = dataclasses.replace(cfg, want_loglik=False)
+        pcfg = dataclasses.replace(cfg, want_loglik=False, tol=max(cfg.tol, cfg.pilot_tol))
         pilot = _newton_fit(make_pass(part_offsets[:Kp + 1]), Kp, p, dev, pcfg, 0, None, whole_batch=False)
         pilot_passes = pilot.passes
         start = _pooled_start(pilot)
