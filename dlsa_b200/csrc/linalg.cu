@@ -59,6 +59,191 @@ __device__ void chol_solve_cta(double* L, int ld, int p, double* x, int* ok_s) {
     }
 }
 
+
+// ---- p > 160: the factor does not fit shared memory; blocked right-looking Cholesky on the copy in global memory ------
+// Panels of 32 columns: (1) the 32x32 diagonal block is factored in shared memory by one warp, (2) every row below
+// solves its 32-column slice against it (one thread per row, the row in registers) and leaves it in a shared-memory
+// panel P, (3) the trailing lower triangle gets  A22 -= P P'  as 8x8 tiles on DMMA (mma.sync m8n8k4 f64; fragments from
+// P with a conflict-free pitch, C tiles straight from / to global memory, 4 independent tiles in flight per warp).
+// 2/3 of the flops of a p=500 factorisation are step (3).  The unblocked rank-1 version this replaces took 68 ms for
+// 1024 matrices of p=500 (C5); see profiles/r01_c5_breakdown.md.
+constexpr int kNB = 32;
+constexpr int kDPitch = 33;
+constexpr int kPPitch = 36;  // == 4 (mod 16) doubles: the (row a8, column q) fragment loads hit 16 distinct banks per half-warp
+
+__device__ void chol_blocked_cta(double* L, int ld, int p, double* x, double* sm, int* ok_s) {
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const int a8 = lane >> 2, q = lane & 3;
+    double* D = sm;
+    double* invd = D + kNB * kDPitch;
+    double* P = invd + kNB;
+    if (tid == 0) *ok_s = 1;
+    __syncthreads();
+    for (int kb = 0; kb < p; kb += kNB) {
+        const int nb = (p - kb < kNB) ? (p - kb) : kNB;
+        const int m = p - kb - nb;            // rows below the panel
+        const int mpad = (m + 7) & ~7;
+        // (1) diagonal block -> shared memory (identity beyond nb), factored by warp 0
+        for (int e = tid; e < kNB * kNB; e += nt) {
+            const int r = e >> 5, c = e & 31;
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < nb && c <= r) v = L[(size_t)(kb + r) * ld + kb + c];
+            D[r * kDPitch + c] = v;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            bool good = true;
+            for (int j = 0; j < kNB; j++) {
+                const double d = D[j * kDPitch + j];
+                if (!(d > 0.0) || !isfinite(d)) { good = false; break; }  // warp-uniform
+                const double dj = sqrt(d);
+                const double lr = (lane > j) ? D[lane * kDPitch + j] / dj : 0.0;
+                __syncwarp();
+                if (lane == j) D[j * kDPitch + j] = dj;
+                if (lane > j) D[lane * kDPitch + j] = lr;
+                __syncwarp();
+                if (lane > j)
+                    for (int c = j + 1; c <= lane; c++)
+                        D[lane * kDPitch + c] = fma(-lr, D[c * kDPitch + j], D[lane * kDPitch + c]);
+                __syncwarp();
+            }
+            if (good) invd[lane] = 1.0 / D[lane * kDPitch + lane];
+            else if (lane == 0) *ok_s = 0;
+        }
+        __syncthreads();
+        if (*ok_s == 0) return;
+        for (int e = tid; e < kNB * kNB; e += nt) {
+            const int r = e >> 5, c = e & 31;
+            if (r < nb && c <= r) L[(size_t)(kb + r) * ld + kb + c] = D[r * kDPitch + c];
+        }
+        if (m == 0) break;
+        // (2) panel: row i solves  x L11' = a  (forward substitution over the 32 columns), x -> global and P
+        for (int ri = tid; ri < mpad; ri += nt) {
+            double xr[kNB];
+            if (ri < m) {
+                double* row = L + (size_t)(kb + nb + ri) * ld + kb;
+#pragma unroll
+                for (int c = 0; c < kNB; c++) xr[c] = (c < nb) ? row[c] : 0.0;
+#pragma unroll
+                for (int c = 0; c < kNB; c++) {
+                    double sacc = xr[c];
+#pragma unroll
+                    for (int t = 0; t < c; t++) sacc = fma(-xr[t], D[c * kDPitch + t], sacc);
+                    xr[c] = sacc * invd[c];
+                }
+#pragma unroll
+                for (int c = 0; c < kNB; c++)
+                    if (c < nb) row[c] = xr[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < kNB; c++) xr[c] = 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < kNB; c++) P[ri * kPPitch + c] = xr[c];
+        }
+        __syncthreads();
+        // (3) trailing update on DMMA: tile (ti, tc), tc <= ti, rows kb+nb+8ti.., columns kb+nb+8tc..
+        const int mt = mpad >> 3;
+        const int ntile = mt * (mt + 1) / 2;
+        const int base = kb + nb;
+        for (int t0 = warp * 4; t0 < ntile; t0 += (nt >> 5) * 4) {
+            double c0[4], c1[4];
+            int gi[4], gc[4], pi[4], pc[4];
+            bool in0[4], in1[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int t = t0 + u;
+                int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+                while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+                while (ti * (ti + 1) / 2 > t) ti--;
+                const int tc = t - ti * (ti + 1) / 2;
+                const bool live = t < ntile;
+                pi[u] = (live ? 8 * ti : 0) + a8;
+                pc[u] = (live ? 8 * tc : 0) + a8;
+                gi[u] = base + (live ? 8 * ti : 0) + a8;
+                gc[u] = base + (live ? 8 * tc : 0) + 2 * q;
+                in0[u] = live && gi[u] < p && gc[u] <= gi[u];
+                in1[u] = live && gi[u] < p && gc[u] + 1 <= gi[u];
+                c0[u] = in0[u] ? L[(size_t)gi[u] * ld + gc[u]] : 0.0;
+                c1[u] = in1[u] ? L[(size_t)gi[u] * ld + gc[u] + 1] : 0.0;
+            }
+#pragma unroll
+            for (int kk = 0; kk < kNB; kk += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const double av = -P[pi[u] * kPPitch + kk + q];
+                    const double bv = P[pc[u] * kPPitch + kk + q];
+                    dmma884(c0[u], c1[u], av, bv);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (in0[u]) L[(size_t)gi[u] * ld + gc[u]] = c0[u];
+                if (in1[u]) L[(size_t)gi[u] * ld + gc[u] + 1] = c1[u];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// x = (L L')^-1 x with the factor in global memory: blocked forward and backward substitution (diagonal block solved by
+// warp 0 with the lane's row / column of the block in registers, the rest of x updated by all threads)
+__device__ void chol_blocked_solve_cta(const double* L, int ld, int p, double* x) {
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    __syncthreads();  // the last diagonal block was written back by all threads
+    for (int kb = 0; kb < p; kb += kNB) {  // forward: L z = b
+        const int nb = (p - kb < kNB) ? (p - kb) : kNB;
+        if (warp == 0) {
+            double lrow[kNB];
+#pragma unroll
+            for (int j = 0; j < kNB; j++) lrow[j] = (lane < nb && j <= lane) ? L[(size_t)(kb + lane) * ld + kb + j] : 1.0;
+            double xr = (lane < nb) ? x[kb + lane] : 0.0;
+#pragma unroll
+            for (int j = 0; j < kNB; j++) {
+                const double djj = __shfl_sync(0xffffffffu, lrow[j], j);
+                const double xj = __shfl_sync(0xffffffffu, xr, j) / djj;
+                if (lane == j) xr = xj;
+                if (lane > j) xr = fma(-lrow[j], xj, xr);
+            }
+            if (lane < nb) x[kb + lane] = xr;
+        }
+        __syncthreads();
+        for (int i = kb + nb + tid; i < p; i += nt) {
+            const double* row = L + (size_t)i * ld + kb;
+            double sacc = 0.0;
+            for (int t = 0; t < nb; t++) sacc = fma(row[t], x[kb + t], sacc);
+            x[i] -= sacc;
+        }
+        __syncthreads();
+    }
+    const int nblk = (p + kNB - 1) / kNB;
+    for (int bi = nblk - 1; bi >= 0; bi--) {  // backward: L' x = z
+        const int kb = bi * kNB;
+        const int nb = (p - kb < kNB) ? (p - kb) : kNB;
+        if (warp == 0) {
+            double lcol[kNB];  // column `lane` of the block: L[kb+j][kb+lane], j >= lane
+#pragma unroll
+            for (int j = 0; j < kNB; j++) lcol[j] = (j < nb && lane <= j) ? L[(size_t)(kb + j) * ld + kb + lane] : 1.0;
+            double xr = (lane < nb) ? x[kb + lane] : 0.0;
+#pragma unroll
+            for (int j = kNB - 1; j >= 0; j--) {
+                const double djj = __shfl_sync(0xffffffffu, lcol[j], j);
+                const double xj = __shfl_sync(0xffffffffu, xr, j) / djj;
+                if (lane == j) xr = xj;
+                if (lane < j && j < nb) xr = fma(-lcol[j], xj, xr);
+            }
+            if (lane < nb) x[kb + lane] = xr;
+        }
+        __syncthreads();
+        for (int c = tid; c < kb; c += nt) {
+            double sacc = 0.0;
+            for (int t = 0; t < nb; t++) sacc = fma(L[(size_t)(kb + t) * ld + c], x[kb + t], sacc);
+            x[c] -= sacc;
+        }
+        __syncthreads();
+    }
+}
+
 // mode 0: Newton update (beta += delta with damping / convergence bookkeeping); mode 1: plain solve
 template <bool SMEM>
 __global__ void __launch_bounds__(kCholThreads) chol_kernel(const double* __restrict__ A, const double* __restrict__ b,
@@ -88,7 +273,12 @@ __global__ void __launch_bounds__(kCholThreads) chol_kernel(const double* __rest
     }
     for (int i = threadIdx.x; i < p; i += blockDim.x) xs[i] = b[(size_t)k * p + i];
     __syncthreads();
-    chol_solve_cta(L, ld, p, xs, &ok_s);
+    if (SMEM) {
+        chol_solve_cta(L, ld, p, xs, &ok_s);
+    } else {
+        chol_blocked_cta(L, ld, p, xs, xs + ((p + 1) & ~1), &ok_s);
+        if (ok_s != 0) chol_blocked_solve_cta(L, ld, p, xs);
+    }
     const bool ok = ok_s != 0;
     if (mode == 1) {
         for (int i = threadIdx.x; i < p; i += blockDim.x) x_out[(size_t)k * p + i] = ok ? xs[i] : 0.0;
@@ -155,7 +345,9 @@ int chol_launch(const double* A, const double* b, int K, int p, int mode, double
         const size_t need = chol_workspace_bytes(K, p);
         DLSA_REQUIRE(workspace != nullptr && workspace_bytes >= need, DLSA_E_WORKSPACE,
                      "cholesky: workspace too small (%zu < %zu)", workspace_bytes, need);
-        const size_t smem = (size_t)((p + 1) & ~1) * sizeof(double);
+        const int mmax = (p > kNB) ? ((p - kNB + 7) & ~7) : 8;
+        const size_t smem = ((size_t)((p + 1) & ~1) + (size_t)kNB * kDPitch + kNB + (size_t)mmax * kPPitch) * sizeof(double);
+        DLSA_CUDA(cudaFuncSetAttribute(chol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         chol_kernel<false><<<K, kCholThreads, smem, st>>>(A, b, K, p, mode, beta, x_out, max_delta, status, active,
                                                           iters, n_active, tol, damp_above, damp_factor,
                                                           static_cast<double*>(workspace));
@@ -226,8 +418,17 @@ __global__ void partition_reduce_kernel(const double* __restrict__ H, const doub
     const int total = p * p + 2 * p + 2;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         double v = 0.0;
-        if (e < p * p) {
-            for (int k = 0; k < K; k++)
+        if (e < p * p) {  // 8 loads in flight, added in the order k = 0..K-1 (x + 0.0 == x: skipped partitions add 0)
+            int k = 0;
+            for (; k + 8 <= K; k += 8) {
+                double t[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    t[u] = (status == nullptr || status[k + u] == DLSA_ST_OK) ? H[(size_t)(k + u) * p * p + e] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) v += t[u];
+            }
+            for (; k < K; k++)
                 if (status == nullptr || status[k] == DLSA_ST_OK) v += H[(size_t)k * p * p + e];
         } else if (e < p * p + p) {
             const int i = e - p * p;

@@ -12,11 +12,15 @@ import torch  # noqa: E402
 from dlsa_b200 import engine, synth  # noqa: E402
 
 n, p, K = 100_000_000, 50, 1024
+if len(sys.argv) == 4:  # python tools/step_breakdown.py <rows> <p> <partitions>
+    n, p, K = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 dev = torch.device("cuda", 0)
 X = torch.empty(n, p, dtype=torch.float64, device=dev)
 y = torch.empty(n, dtype=torch.float64, device=dev)
+bt = synth.true_beta(p) * (0.2 if p > 60 else 1.0)
 for s in range(0, n, 10_000_000):
-    synth.simulate_logistic_device(10_000_000, p, 20210517, dev, row0=s, out=(X[s:s + 10_000_000], y[s:s + 10_000_000]))
+    m = min(10_000_000, n - s)
+    synth.simulate_logistic_device(m, p, 20210517, dev, row0=s, beta=bt, out=(X[s:s + m], y[s:s + m]))
 off = synth.equal_partition_offsets(n, K, dev)
 
 
