@@ -81,6 +81,86 @@ __device__ void backward_solve_w0(const double* R, int a, int m, double* x) {
     __syncthreads();
 }
 
+// ---- blocked versions for a large active set (R in global memory, a > kBlkMin): 32-column blocks; the diagonal block is
+// solved by warp 0 with the lane's column / row of the block in registers, the rest of x is updated by ALL threads with
+// 32 independent loads each.  The warp-0 versions above walk the packed factor one dependent global load per column:
+// ~200 us per solve at a = 500, three solves per LARS step (C5: 415 ms for the 501-knot path).
+constexpr int kBlk = 32;
+constexpr int kBlkMin = 64;
+
+// solve R' r = x in place
+__device__ void forward_solve_blk(const double* R, int a, int m, double* x) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    for (int kb = 0; kb < a; kb += kBlk) {
+        const int nb = (a - kb < kBlk) ? (a - kb) : kBlk;
+        if (tid < 32) {
+            double col[kBlk];  // column `lane` of the diagonal block: R[kb+t][kb+lane], t <= lane
+#pragma unroll
+            for (int t = 0; t < kBlk; t++) col[t] = (lane < nb && t <= lane) ? R[rpk(kb + t, kb + lane, m)] : 1.0;
+            double xr = (lane < nb) ? x[kb + lane] : 0.0;
+#pragma unroll
+            for (int t = 0; t < kBlk; t++) {
+                const double d = __shfl_sync(0xffffffffu, col[t], t);
+                const double xt = __shfl_sync(0xffffffffu, xr, t) / d;
+                if (lane == t) xr = xt;
+                if (lane > t) xr = fma(-col[t], xt, xr);
+            }
+            if (lane < nb) x[kb + lane] = xr;
+        }
+        __syncthreads();
+        for (int i = kb + nb + tid; i < a; i += nt) {
+            double sacc = 0.0;
+#pragma unroll 8
+            for (int t = 0; t < nb; t++) sacc = fma(R[rpk(kb + t, i, m)], x[kb + t], sacc);
+            x[i] -= sacc;
+        }
+        __syncthreads();
+    }
+}
+
+// solve R z = x in place
+__device__ void backward_solve_blk(const double* R, int a, int m, double* x) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int nblk = (a + kBlk - 1) / kBlk;
+    for (int bi = nblk - 1; bi >= 0; bi--) {
+        const int kb = bi * kBlk;
+        const int nb = (a - kb < kBlk) ? (a - kb) : kBlk;
+        if (tid < 32) {
+            double row[kBlk];  // row `lane` of the diagonal block: R[kb+lane][kb+s], s >= lane
+#pragma unroll
+            for (int sidx = 0; sidx < kBlk; sidx++)
+                row[sidx] = (sidx < nb && lane <= sidx) ? R[rpk(kb + lane, kb + sidx, m)] : 1.0;
+            double xr = (lane < nb) ? x[kb + lane] : 0.0;
+#pragma unroll
+            for (int sidx = kBlk - 1; sidx >= 0; sidx--) {
+                const double d = __shfl_sync(0xffffffffu, row[sidx], sidx);
+                const double zs = __shfl_sync(0xffffffffu, xr, sidx) / d;
+                if (lane == sidx) xr = zs;
+                if (lane < sidx && sidx < nb) xr = fma(-row[sidx], zs, xr);
+            }
+            if (lane < nb) x[kb + lane] = xr;
+        }
+        __syncthreads();
+        for (int l = tid; l < kb; l += nt) {
+            const double* rl = R + rpk(l, kb, m);
+            double sacc = 0.0;
+#pragma unroll 8
+            for (int t = 0; t < nb; t++) sacc = fma(rl[t], x[kb + t], sacc);
+            x[l] -= sacc;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void forward_solve(const double* R, int a, int m, double* x) {
+    if (a > kBlkMin) forward_solve_blk(R, a, m, x);
+    else forward_solve_w0(R, a, m, x);
+}
+__device__ __forceinline__ void backward_solve(const double* R, int a, int m, double* x) {
+    if (a > kBlkMin) backward_solve_blk(R, a, m, x);
+    else backward_solve_w0(R, a, m, x);
+}
+
 // warp 0: delete column kdel of R (a x a) and restore triangularity with Givens rotations (dlsa/lsa.py:35-71)
 __device__ void delete_column_w0(double* R, int a, int m, int kdel) {
     if (threadIdx.x < 32) {
@@ -243,7 +323,7 @@ __global__ void __launch_bounds__(kLarsThreads, 1) lars_path_kernel(const LarsAr
                 }
                 for (int l = tid; l < na; l += nt) tmp[l] = a.Sig[(size_t)inew * m + act[l]];
                 __syncthreads();
-                forward_solve_w0(R, na, m, tmp);  // updateR: r = backsolvet(R, xold)  (:19)
+                forward_solve(R, na, m, tmp);  // updateR: r = backsolvet(R, xold)  (:19)
                 double part = 0.0;
                 for (int l = tid; l < na; l += nt) part = fma(tmp[l], tmp[l], part);
                 const double ss = block_sum(part, sh.red);
@@ -273,8 +353,8 @@ __global__ void __launch_bounds__(kLarsThreads, 1) lars_path_kernel(const LarsAr
         // equiangular direction: Gi1 = R^-1 R^-T Sign, A = 1/sqrt(Gi1.Sign), w = A Gi1 (:151-153)
         for (int l = tid; l < na; l += nt) tmp[l] = Sign[l];
         __syncthreads();
-        forward_solve_w0(R, na, m, tmp);
-        backward_solve_w0(R, na, m, tmp);
+        forward_solve(R, na, m, tmp);
+        backward_solve(R, na, m, tmp);
         double part = 0.0;
         for (int l = tid; l < na; l += nt) part = fma(tmp[l], Sign[l], part);
         const double gs = block_sum(part, sh.red);
