@@ -559,6 +559,10 @@ static TiledCfg tiled_cfg(int px, int p) {
             if (mask == 0xffu) full.push_back({m, J, mask, false});
             else part.push_back({m, J, mask, m == mg});
         }
+    // (Tried and measured slower: one body per BLOCK instead of per (full-block count, partial shape), blocks run one
+    // after the other, so that any mix of shapes can share a warp and the deal can equalise tiles per warp (p=100: 7..8
+    // instead of 4..11).  C4 22.9 -> 25.2 ms, p=100 logistic 25.4 -> 29.1, C5 28.2 -> 29.8: the interleaved body keeps 24
+    // independent DMMAs and all fragment loads of a k-step in flight, which is worth more than the balance.)
     // Siblings: enough MMA warps for one partial block each and enough slots for everything.  The FP64 pipe is per
     // sub-partition, so what has to be equal is the number of DMMAs per (sibling, sub-partition) bin: all blocks,
     // heaviest first (full blocks, then partial ones by tile count), each to the least-loaded bin that can still take
@@ -673,13 +677,20 @@ static size_t tiled_slice_bytes(int K, int S, int p) {
     return S == 1 ? 0 : (size_t)K * S * ((size_t)p * p + p + 1) * sizeof(double);
 }
 
+// The streaming link kernel addresses its w / r / log-lik buffers by global row, and the host only knows the bound
+// K * max_part_rows for the row count.  With very ragged partitions that bound can dwarf the data; past 16 GB the fused
+// link warps are used instead (same results, slower at large p).
+static bool tiled_use_pre(const TiledCfg& c, int K, int64_t max_part_rows) {
+    return c.pre && 3.0 * sizeof(double) * (double)K * (double)max_part_rows <= 16.0 * 1024 * 1024 * 1024;
+}
+
 // workspace = [slice partials | w, r, ll of every row (PRE mode; rows <= K * max_part_rows)]
 size_t irls_tiled_workspace_bytes(int K, int p, int64_t max_part_rows) {
     if (p > kTiledMaxP) return 0;
     TiledCfg c = tiled_cfg(p, p);
     const int S = tiled_slices(K, c.TG, c.CH, max_part_rows);
     size_t need = tiled_slice_bytes(K, S, p);
-    if (c.pre) need += 3 * (size_t)K * (size_t)max_part_rows * sizeof(double);
+    if (tiled_use_pre(c, K, max_part_rows)) need += 3 * (size_t)K * (size_t)max_part_rows * sizeof(double);
     return need;
 }
 
@@ -703,7 +714,7 @@ int irls_tiled_launch(const double* X, int64_t ldx, const double* y, const int64
     double *pH = nullptr, *pg = nullptr, *pll = nullptr;
     const bool glm = family != DLSA_FAMILY_LINEAR;  // logistic or Poisson: the GLM instantiation, link chosen at run time
     a.poisson = family == DLSA_FAMILY_POISSON ? 1 : 0;
-    const bool pre = c.pre && glm;
+    const bool pre = glm && tiled_use_pre(c, K, max_part_rows);
     const size_t slice_bytes = tiled_slice_bytes(K, S, p);
     const size_t need = slice_bytes + (pre ? 3 * (size_t)K * (size_t)max_part_rows * sizeof(double) : 0);
     DLSA_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need), DLSA_E_WORKSPACE,
