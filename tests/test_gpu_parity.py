@@ -469,3 +469,38 @@ def test_poisson_dlsa_end_to_end(eng):
     assert np.array_equal(path.beta.cpu().numpy() != 0, rp["beta"] != 0)
     assert path.argmin_BIC == int(np.argmin(rp["BIC"]))
     assert np.array_equal(path.beta[path.argmin_BIC].cpu().numpy() != 0, truth != 0)
+
+
+@pytest.mark.parametrize("p", [1, 7, 50, 160, 161, 192, 200, 333, 500, 512])
+def test_batched_spd_solve_matches_lapack(eng, p):
+    """K5 / the solve inside K2 (np.linalg.lstsq(Sig_inv_sum, ...) of dlsa/dlsa.py:48; solve(hess) of
+    dlsa/R/wlse_func.R:55): shared-memory factorisation up to p = 160, blocked DMMA factorisation of the global-memory
+    copy above (panels of 32: p = 161, 192, 200, 333 hit ragged last panels and ragged 8x8 tiles).  A matrix that loses
+    positive definiteness at a late pivot must come back as ST_NOT_SPD, the others untouched."""
+    from dlsa_b200 import _lib
+    from dlsa_b200._lib import lib, check
+    rng = np.random.default_rng(p)
+    K = 5
+    A = np.empty((K, p, p))
+    for k in range(K):
+        M = rng.standard_normal((p + 3, p))
+        A[k] = M.T @ M + 0.1 * np.eye(p)
+    bad = 3
+    if p >= 2:
+        A[bad, p - 1, p - 1] = -1.0   # indefinite only in the very last pivot
+    b = rng.standard_normal((K, p))
+    Ad, bd = dev(A), dev(b)
+    x = torch.empty(K, p, dtype=torch.float64, device="cuda")
+    st = torch.full((K,), -7, dtype=torch.int32, device="cuda")
+    ws = eng._workspace(lib.dlsa_newton_update_workspace_bytes(K, p), Ad.device)
+    check(lib.dlsa_spd_solve_f64(Ad.data_ptr(), bd.data_ptr(), K, p, x.data_ptr(), st.data_ptr(), ws.data_ptr(),
+                                 ws.numel(), torch.cuda.current_stream().cuda_stream), "dlsa_spd_solve_f64")
+    st = st.cpu().numpy()
+    for k in range(K):
+        if k == bad and p >= 2:
+            assert st[k] == _lib.ST_NOT_SPD
+            continue
+        assert st[k] == _lib.ST_OK
+        ref = np.linalg.solve(A[k], b[k])
+        assert np.max(np.abs(x[k].cpu().numpy() - ref)) <= 1e-9 * max(1.0, np.max(np.abs(ref))), (k, p)
+    assert torch.equal(Ad, dev(A))  # the input matrices are not modified
