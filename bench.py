@@ -276,6 +276,17 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
+            # every rank pins its whole shard (40.8 GB at C2): make sure the box has the host memory for all local
+            # ranks before asking for it — an out-of-memory kill would take the whole run down
+            try:
+                import psutil
+                need = world * (n * (p + 1) * 8) * 1.15
+                avail = psutil.virtual_memory().available
+                if avail < need:
+                    raise MemoryError(f"host memory: {avail / 1e9:.0f} GB available, {need / 1e9:.0f} GB needed to pin "
+                                      f"{world} shards")
+            except ImportError:
+                pass
             Xh = torch.empty(n, p, dtype=torch.float64, pin_memory=True)
             yh = torch.empty(n, dtype=torch.float64, pin_memory=True)
             Xh.copy_(X)
