@@ -277,16 +277,24 @@ def main():
     if not args.no_e2e:
         try:
             # every rank pins its whole shard (40.8 GB at C2): make sure the box has the host memory for all local
-            # ranks before asking for it — an out-of-memory kill would take the whole run down
+            # ranks before any of them asks for it (an out-of-memory kill would take the whole run down); the decision
+            # is taken collectively so that no rank waits at a barrier the others skipped
+            barrier()
+            mem_ok, mem_msg = 1, ""
             try:
                 import psutil
                 need = world * (n * (p + 1) * 8) * 1.15
                 avail = psutil.virtual_memory().available
                 if avail < need:
-                    raise MemoryError(f"host memory: {avail / 1e9:.0f} GB available, {need / 1e9:.0f} GB needed to pin "
-                                      f"{world} shards")
+                    mem_ok = 0
+                    mem_msg = f"host memory: {avail / 1e9:.0f} GB available, {need / 1e9:.0f} GB needed to pin {world} shards"
             except ImportError:
                 pass
+            flag = torch.tensor([mem_ok], dtype=torch.int32, device=dev)
+            if world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                raise MemoryError(mem_msg or "another rank reported too little host memory to pin its shard")
             Xh = torch.empty(n, p, dtype=torch.float64, pin_memory=True)
             yh = torch.empty(n, dtype=torch.float64, pin_memory=True)
             Xh.copy_(X)
