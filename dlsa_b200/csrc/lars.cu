@@ -98,10 +98,13 @@ __device__ void forward_solve_blk(const double* R, int a, int m, double* x) {
 #pragma unroll
             for (int t = 0; t < kBlk; t++) col[t] = (lane < nb && t <= lane) ? R[rpk(kb + t, kb + lane, m)] : 1.0;
             double xr = (lane < nb) ? x[kb + lane] : 0.0;
+            double rd = 1.0;  // 1 / R[kb+lane][kb+lane]: one division per lane instead of one per column on the chain
+#pragma unroll
+            for (int t = 0; t < kBlk; t++)
+                if (lane == t) rd = 1.0 / col[t];
 #pragma unroll
             for (int t = 0; t < kBlk; t++) {
-                const double d = __shfl_sync(0xffffffffu, col[t], t);
-                const double xt = __shfl_sync(0xffffffffu, xr, t) / d;
+                const double xt = __shfl_sync(0xffffffffu, xr * rd, t);
                 if (lane == t) xr = xt;
                 if (lane > t) xr = fma(-col[t], xt, xr);
             }
@@ -131,10 +134,13 @@ __device__ void backward_solve_blk(const double* R, int a, int m, double* x) {
             for (int sidx = 0; sidx < kBlk; sidx++)
                 row[sidx] = (sidx < nb && lane <= sidx) ? R[rpk(kb + lane, kb + sidx, m)] : 1.0;
             double xr = (lane < nb) ? x[kb + lane] : 0.0;
+            double rd = 1.0;
+#pragma unroll
+            for (int sidx = 0; sidx < kBlk; sidx++)
+                if (lane == sidx) rd = 1.0 / row[sidx];
 #pragma unroll
             for (int sidx = kBlk - 1; sidx >= 0; sidx--) {
-                const double d = __shfl_sync(0xffffffffu, row[sidx], sidx);
-                const double zs = __shfl_sync(0xffffffffu, xr, sidx) / d;
+                const double zs = __shfl_sync(0xffffffffu, xr * rd, sidx);
                 if (lane == sidx) xr = zs;
                 if (lane < sidx && sidx < nb) xr = fma(-row[sidx], zs, xr);
             }
@@ -298,13 +304,25 @@ __global__ void __launch_bounds__(kLarsThreads, 1) lars_path_kernel(const LarsAr
         const double Cmax = block_reduce(cm, true, sh.red);
         (void)any_inactive;
         if (!sh.drops_pending) {
-            // joiners in ascending index order (:131-133)
-            if (tid == 0) {
-                int nj = 0;
-                for (int j = 0; j < m; j++)
-                    if (state[j] == 0 && fabs(Cvec[j]) >= Cmax - eps) joiners[nj++] = j;
-                sh.n_join = nj;
+            // joiners in ascending index order (:131-133): ballot per warp, prefix over the warps
+            int jbase = 0;
+            for (int j0 = 0; j0 < m; j0 += nt) {
+                const int j = j0 + tid;
+                const bool f = j < m && state[j] == 0 && fabs(Cvec[j]) >= Cmax - eps;
+                const unsigned bal = __ballot_sync(0xffffffffu, f);
+                if ((tid & 31) == 0) sh.ired[tid >> 5] = __popc(bal);
+                __syncthreads();
+                int before = 0, tot = 0;
+                for (int wq = 0; wq < kLarsThreads / 32; wq++) {
+                    const int cq = sh.ired[wq];
+                    before += (wq < (tid >> 5)) ? cq : 0;
+                    tot += cq;
+                }
+                if (f) joiners[jbase + before + __popc(bal & ((1u << (tid & 31)) - 1u))] = j;
+                jbase += tot;
+                __syncthreads();
             }
+            if (tid == 0) sh.n_join = jbase;
             __syncthreads();
             for (int jn = 0; jn < sh.n_join; jn++) {
                 const int inew = joiners[jn];
