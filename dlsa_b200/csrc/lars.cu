@@ -548,7 +548,8 @@ int lars_launch(const double* Sigma0, const double* b0, int p0, int intercept, d
     count_launch();
     int rc = check_launch("lars_path_kernel");
     if (rc) return rc;
-    lars_ic_kernel<<<a.max_steps + 1, 256, (size_t)m * 8, st>>>(a);
+    // rounded up to 16 bytes: the compiler reads d_s two doubles at a time (LDS.128), also across the end of an odd m
+    lars_ic_kernel<<<a.max_steps + 1, 256, (size_t)((m + 1) & ~1) * 8, st>>>(a);
     count_launch();
     rc = check_launch("lars_ic_kernel");
     if (rc) return rc;
