@@ -109,3 +109,26 @@ def test_synth_host_restatement_is_deterministic():
     sizes = (off[1:] - off[:-1])
     assert int(off[-1]) == 100_000_000 and int(sizes.max()) == 97657 and int(sizes.min()) == 97656
     assert np.array_equal(synth.true_beta(50), np.r_[np.ones(20), np.zeros(30)])
+
+
+def test_bench_contract_reference_arm_and_no_gpu_failure():
+    """bench.py --impl reference runs the reference's CPU path (oracle/ref_port.py) and prints ONE JSON line with the
+    contract's keys; without a GPU the product arm must fail loudly instead of falling back to anything."""
+    import json
+    import sys
+    bench = os.path.join(ROOT, "bench.py")
+    out = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "0", "--rows", "32000",
+                          "--parts", "16", "--cpu-parts", "4", "--p", "6"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "dlsa_rows_per_sec" and d["unit"] == "rows/s" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "port"
+    if not torch.cuda.is_available():
+        out = subprocess.run([sys.executable, bench, "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                             timeout=300)
+        assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
