@@ -725,11 +725,21 @@ int irls_tiled_launch(const double* X, int64_t ldx, const double* y, const int64
         double* rbuf = wbuf + (size_t)K * max_part_rows;
         double* lbuf = rbuf + (size_t)K * max_part_rows;
         a.pre_w = wbuf; a.pre_r = rbuf; a.pre_ll = a.want_ll ? lbuf : nullptr;
-        int gx = (int)((max_part_rows + kLinkWarps * 32 - 1) / (kLinkWarps * 32));
-        const int gx_cap = (148 * 8 + K - 1) / K;
-        if (gx > gx_cap) gx = gx_cap;
-        if (gx < 1) gx = 1;
         const size_t lsm = ((size_t)32 * ((px + 31) / 32) + kLinkWarps * 32) * sizeof(double);
+        // one wave: as many CTAs per partition as keep every SM's resident slots filled, no partial second wave
+        int resident = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, tiled_link_kernel, kLinkWarps * 32, lsm) != cudaSuccess ||
+            resident < 1)
+            resident = 4;
+        const int gx_max = (int)((max_part_rows + kLinkWarps * 32 - 1) / (kLinkWarps * 32));
+        const int slots = 148 * resident;
+        int gx = 1;
+        double best = -1.0;
+        for (int cand = 1; cand <= gx_max && (int64_t)K * cand <= 4 * (int64_t)slots + K; cand++) {
+            const int64_t ctas = (int64_t)K * cand;
+            const double eff = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
+            if (eff > best + 0.02) { best = eff; gx = cand; }  // more CTAs per partition must buy > 2 % of wave efficiency
+        }
         tiled_link_kernel<<<dim3(gx, K), kLinkWarps * 32, lsm, st>>>(X, ldx, y, part_off, beta, active, px, a.icpt,
                                                                      a.poisson, wbuf, rbuf, a.want_ll ? lbuf : nullptr);
         count_launch();
