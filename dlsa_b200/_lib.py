@@ -53,6 +53,7 @@ SIGNATURES = {
     "dlsa_logistic_loglik_f64": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "dlsa_simulate_f64": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp, _u64, _i, _vp]),
     "dlsa_onehot_expand_f64": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp, _i64, _vp]),
+    "dlsa_irls_tiled_schedule": (_i, [_i, _i, _vp, _vp]),
     "dlsa_column_stats_workspace_bytes": (_sz, [_i]),
     "dlsa_column_stats_f64": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _sz, _vp]),
 }

@@ -49,6 +49,7 @@ int loglik_launch(const double*, int64_t, const double*, const int64_t*, int, in
 int onehot_launch(const double*, int, const double*, const double*, const int*, int, const int*, int64_t, double*,
                   int64_t, cudaStream_t);
 
+int irls_tiled_schedule_info(int px, int icpt, uint32_t* sched_out, int* info);
 size_t colstats_workspace_bytes(int px);
 int colstats_launch(const double*, int64_t, int64_t, int, double*, double*, cudaStream_t);
 
@@ -198,6 +199,13 @@ int dlsa_onehot_expand_f64(const double* numeric, int n_num, const double* mean,
     DLSA_REQUIRE((n_num == 0 || numeric) && (n_cat == 0 || (codes && col_base)), DLSA_E_BADARG, "onehot: null pointer");
     DLSA_REQUIRE((mean == nullptr) == (std == nullptr), DLSA_E_BADARG, "onehot: mean/std must both be given");
     return onehot_launch(numeric, n_num, mean, std, codes, n_cat, col_base, n, X, ldx, static_cast<cudaStream_t>(stream));
+}
+
+int dlsa_irls_tiled_schedule(int px, int fit_intercept, uint32_t* sched_out, int* info) {
+    DLSA_REQUIRE(sched_out && info, DLSA_E_BADARG, "tiled schedule: null pointer");
+    DLSA_REQUIRE(irls_tiled_schedule_info(px, fit_intercept ? 1 : 0, sched_out, info) == 0, DLSA_E_UNSUPPORTED,
+                 "tiled schedule: p must be in 57..512");
+    return 0;
 }
 
 size_t dlsa_column_stats_workspace_bytes(int px) { return px <= 0 ? 0 : colstats_workspace_bytes(px); }

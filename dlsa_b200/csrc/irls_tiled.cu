@@ -680,6 +680,19 @@ static size_t tiled_slice_bytes(int K, int S, int p) {
 // The streaming link kernel addresses its w / r / log-lik buffers by global row, and the host only knows the bound
 // K * max_part_rows for the row count.  With very ragged partitions that bound can dwarf the data; past 16 GB the fused
 // link warps are used instead (same results, slower at large p).
+// Host-only diagnostic behind dlsa_irls_tiled_schedule (include/dlsa_b200.h): the block schedule and ring geometry
+// the tiled kernel would use for this shape.  tests/test_abi_and_host.py checks on the CPU, for every p, that each
+// lower-triangle tile has exactly one owner and that the ring fits shared memory.
+int irls_tiled_schedule_info(int px, int icpt, uint32_t* sched_out, int* info) {
+    const int p = px + (icpt ? 1 : 0);
+    if (p <= 56 || p > kTiledMaxP) return -1;
+    TiledCfg c = tiled_cfg(px, p);
+    for (size_t i = 0; i < c.sched.size(); i++) sched_out[i] = c.sched[i];
+    info[0] = c.NT; info[1] = c.TG; info[2] = c.CH; info[3] = c.stages; info[4] = c.pre; info[5] = c.Sd;
+    info[6] = (int)c.smem; info[7] = kTMma * kTNBW;
+    return 0;
+}
+
 static bool tiled_use_pre(const TiledCfg& c, int K, int64_t max_part_rows) {
     return c.pre && 3.0 * sizeof(double) * (double)K * (double)max_part_rows <= 16.0 * 1024 * 1024 * 1024;
 }

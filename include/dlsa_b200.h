@@ -186,6 +186,14 @@ int dlsa_simulate_f64(double *X, int64_t ldx, double *y, int64_t row0, int64_t n
 int dlsa_onehot_expand_f64(const double *numeric, int n_num, const double *mean, const double *std, const int *codes,
                            int n_cat, const int *col_base, int64_t n, double *X, int64_t ldx, void *stream);
 
+/* Diagnostic (host only, no GPU needed): the block schedule of the tiled fused pass for p = px + fit_intercept in
+ *   57..512.  sched_out [16 * 12 * 3] words, entry (sibling CTA, MMA warp, slot): bits 0-7 = valid-tile mask of a block
+ *   of 2 tile rows x 4 tile columns (bit 4*ii + jj), 8-15 = row pair m (tile rows 2m, 2m+1), 16-23 = column group J
+ *   (tile columns 4J..4J+3), 24 = owns the gradient of its column group, 0 = empty slot.
+ *   info [8]: tile rows NT, sibling CTAs TG, rows per chunk, ring stages, streaming-link flag, row pitch (doubles),
+ *   dynamic shared memory (bytes), slots per CTA. */
+int dlsa_irls_tiled_schedule(int px, int fit_intercept, uint32_t *sched_out, int *info);
+
 /* f-3  describe(): count, mean, sample standard deviation, min, max of every column of X [n, ldx] in one streaming
  *   pass — the statistics the reference takes from Spark's data_sdf_i.describe() (projects/logistic_dlsa.py:279-283)
  *   and applies as (x - mean) / stddev in logistic_model (dlsa/models.py:99-101).

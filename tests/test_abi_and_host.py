@@ -132,3 +132,49 @@ def test_bench_contract_reference_arm_and_no_gpu_failure():
         out = subprocess.run([sys.executable, bench, "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
                              timeout=300)
         assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_tiled_schedule_covers_every_tile_exactly_once():
+    """The tiled fused pass gives every 8x8 tile of the lower triangle of H to exactly one (sibling CTA, warp, slot) —
+    that is what makes it reduction-free and bitwise reproducible.  Checked on the CPU for every p the kernel accepts,
+    together with the ring geometry (>= 3 stages, a multiple of the 3 link warps, within 227 KB of shared memory)."""
+    import ctypes as C
+    from dlsa_b200 import _lib
+    sched = (C.c_uint32 * (16 * 12 * 3))()
+    info = (C.c_int * 8)()
+    assert _lib.lib.dlsa_irls_tiled_schedule(56, 0, sched, info) != 0       # p <= 56 belongs to the small kernel
+    assert _lib.lib.dlsa_irls_tiled_schedule(513, 0, sched, info) != 0
+    for px in list(range(57, 513)):
+        for icpt in ((0, 1) if px % 37 == 0 or px in (57, 181, 511) else (0,)):
+            p = px + icpt
+            if p > 512:
+                continue
+            assert _lib.lib.dlsa_irls_tiled_schedule(px, icpt, sched, info) == 0, (px, icpt)
+            NT, TG, CH, stages, pre, Sd, smem, slots = list(info)
+            assert NT == (p + 7) // 8 and 1 <= TG <= 16 and CH in (16, 32)
+            assert stages >= 3 and stages % 3 == 0 and smem <= 227 * 1024
+            assert Sd % 16 == 4 and Sd >= px + 1 and Sd >= 32 * ((NT + 3) // 4)
+            assert pre == (1 if TG >= 2 else 0)
+            owner = np.zeros((NT, NT), dtype=np.int32)
+            g_owner = np.zeros((NT + 3) // 4, dtype=np.int32)
+            per_warp_partials = {}
+            for idx in range(TG * 12 * 3):
+                e = sched[idx]
+                mask, m, J, g = e & 0xFF, (e >> 8) & 0xFF, (e >> 16) & 0xFF, (e >> 24) & 1
+                if mask == 0:
+                    assert e == 0
+                    continue
+                if mask != 0xFF:
+                    per_warp_partials[idx // 3] = per_warp_partials.get(idx // 3, 0) + 1
+                for ii in range(2):
+                    for jj in range(4):
+                        if mask & (1 << (4 * ii + jj)):
+                            i, j = 2 * m + ii, 4 * J + jj
+                            assert i < NT and j <= i, (p, i, j)
+                            owner[i, j] += 1
+                g_owner[J] += g
+            assert all(sched[idx] == 0 for idx in range(TG * 12 * 3, 16 * 12 * 3))
+            lower = np.tril(np.ones((NT, NT), dtype=np.int32))
+            assert np.array_equal(owner, lower), p                 # every lower-triangle tile exactly once, nothing else
+            assert np.all(g_owner == 1), p                        # every column group's gradient has one owner
+            assert max(per_warp_partials.values(), default=0) <= 1  # the body handles one partial block per warp
