@@ -64,11 +64,12 @@ __device__ void chol_solve_cta(double* L, int ld, int p, double* x, int* ok_s) {
 // Panels of 32 columns: (1) the 32x32 diagonal block is factored in shared memory by one warp, (2) every row below
 // solves its 32-column slice against it (one thread per row, the row in registers) and leaves it in a shared-memory
 // panel P, (3) the trailing lower triangle gets  A22 -= P P'  as 8x8 tiles on DMMA (mma.sync m8n8k4 f64; fragments from
-// P with a conflict-free pitch, C tiles straight from / to global memory, 4 independent tiles in flight per warp).
+// P with a conflict-free pitch, C tiles straight from / to global memory, kTIF independent tiles in flight per warp).
 // 2/3 of the flops of a p=500 factorisation are step (3).  The unblocked rank-1 version this replaces took 68 ms for
 // 1024 matrices of p=500 (C5); see profiles/r01_c5_breakdown.md.
 constexpr int kNB = 32;
 constexpr int kDPitch = 33;
+constexpr int kTIF = 8;      // 8x8 tiles in flight per warp in the trailing update (independent C loads and DMMA chains)
 constexpr int kPPitch = 36;  // == 4 (mod 16) doubles: the (row a8, column q) fragment loads hit 16 distinct banks per half-warp
 
 __device__ void chol_blocked_cta(double* L, int ld, int p, double* x, double* sm, int* ok_s) {
@@ -146,12 +147,12 @@ __device__ void chol_blocked_cta(double* L, int ld, int p, double* x, double* sm
         const int mt = mpad >> 3;
         const int ntile = mt * (mt + 1) / 2;
         const int base = kb + nb;
-        for (int t0 = warp * 4; t0 < ntile; t0 += (nt >> 5) * 4) {
-            double c0[4], c1[4];
-            int gi[4], gc[4], pi[4], pc[4];
-            bool in0[4], in1[4];
+        for (int t0 = warp * kTIF; t0 < ntile; t0 += (nt >> 5) * kTIF) {
+            double c0[kTIF], c1[kTIF];
+            int gi[kTIF], gc[kTIF], pi[kTIF], pc[kTIF];
+            bool in0[kTIF], in1[kTIF];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < kTIF; u++) {
                 const int t = t0 + u;
                 int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
                 while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
@@ -170,14 +171,14 @@ __device__ void chol_blocked_cta(double* L, int ld, int p, double* x, double* sm
 #pragma unroll
             for (int kk = 0; kk < kNB; kk += 4) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < kTIF; u++) {
                     const double av = -P[pi[u] * kPPitch + kk + q];
                     const double bv = P[pc[u] * kPPitch + kk + q];
                     dmma884(c0[u], c1[u], av, bv);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < kTIF; u++) {
                 if (in0[u]) L[(size_t)gi[u] * ld + gc[u]] = c0[u];
                 if (in1[u]) L[(size_t)gi[u] * ld + gc[u] + 1] = c1[u];
             }
