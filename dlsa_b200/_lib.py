@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdlsa_b200.so")
+# DLSA_B200_LIB: tooling only (tools/k1_variants.sh times experimental builds of the same ABI side by side)
+LIB_PATH = os.environ.get("DLSA_B200_LIB") or os.path.join(_HERE, "libdlsa_b200.so")
 
 ABI_VERSION = 1
 ST_OK, ST_NOT_CONVERGED, ST_NOT_SPD, ST_SKIPPED = 0, 1, 2, 4
@@ -52,6 +53,8 @@ SIGNATURES = {
     "dlsa_logistic_loglik_workspace_bytes": (_sz, [_i, _i]),
     "dlsa_logistic_loglik_f64": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "dlsa_simulate_f64": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp, _u64, _i, _vp]),
+    "dlsa_simulate_airline_f64": (_i, [_vp, _i64, _vp, _vp, _i64, _i64, _i, _i, _vp, _vp, _d, _vp, _vp, _u64, _vp]),
+    "dlsa_probe_fp64_dmma": (_i, [_i, _i, _vp, _vp, _vp]),
     "dlsa_onehot_expand_f64": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp, _i64, _vp]),
     "dlsa_irls_tiled_schedule": (_i, [_i, _i, _vp, _vp]),
     "dlsa_column_stats_workspace_bytes": (_sz, [_i]),

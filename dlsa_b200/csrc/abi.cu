@@ -43,6 +43,9 @@ size_t lars_workspace_bytes(int p0, int max_steps);
 int lars_launch(const double*, const double*, int, int, double, int, double, int, double*, double*, double*, double*,
                 double*, int*, int*, void*, size_t, cudaStream_t);
 int simulate_launch(double*, int64_t, double*, int64_t, int64_t, int, const double*, uint64_t, int, cudaStream_t);
+int airline_launch(double*, int64_t, int*, double*, int64_t, int64_t, int, int, const int*, const double*, double,
+                   const double*, const double*, uint64_t, cudaStream_t);
+int fp64_probe_launch(int, int, double*, cudaStream_t);
 int loglik_slices(int K);
 int loglik_launch(const double*, int64_t, const double*, const int64_t*, int, int, int, const double*, int, double*,
                   double*, cudaStream_t);
@@ -193,12 +196,28 @@ int dlsa_simulate_f64(double* X, int64_t ldx, double* y, int64_t row0, int64_t n
     return simulate_launch(X, ldx, y, row0, n, px, beta_true, seed, law, static_cast<cudaStream_t>(stream));
 }
 
+int dlsa_simulate_airline_f64(double* numeric, int64_t ldn, int* codes, double* y, int64_t row0, int64_t n, int n_num,
+                              int n_cat, const int* levels_dev, const double* cdf_dev, double beta0,
+                              const double* beta_num_dev, const double* beta_lev_dev, uint64_t seed, void* stream) {
+    DLSA_REQUIRE(codes && y && levels_dev && cdf_dev && beta_lev_dev && n >= 0 && n_num >= 0 && n_cat >= 1 &&
+                     ldn >= n_num && (n_num == 0 || (numeric && beta_num_dev)),
+                 DLSA_E_BADARG, "simulate airline: bad argument");
+    return airline_launch(numeric, ldn, codes, y, row0, n, n_num, n_cat, levels_dev, cdf_dev, beta0, beta_num_dev,
+                          beta_lev_dev, seed, static_cast<cudaStream_t>(stream));
+}
+
 int dlsa_onehot_expand_f64(const double* numeric, int n_num, const double* mean, const double* std, const int* codes,
                            int n_cat, const int* col_base, int64_t n, double* X, int64_t ldx, void* stream) {
     DLSA_REQUIRE(X && n >= 0 && n_num >= 0 && n_cat >= 0, DLSA_E_BADARG, "onehot: bad argument");
     DLSA_REQUIRE((n_num == 0 || numeric) && (n_cat == 0 || (codes && col_base)), DLSA_E_BADARG, "onehot: null pointer");
     DLSA_REQUIRE((mean == nullptr) == (std == nullptr), DLSA_E_BADARG, "onehot: mean/std must both be given");
     return onehot_launch(numeric, n_num, mean, std, codes, n_cat, col_base, n, X, ldx, static_cast<cudaStream_t>(stream));
+}
+
+int dlsa_probe_fp64_dmma(int ctas, int iters, double* sink, double* flops_out, void* stream) {
+    DLSA_REQUIRE(ctas >= 1 && iters >= 1 && sink && flops_out, DLSA_E_BADARG, "fp64 probe: bad argument");
+    *flops_out = (double)ctas * 16.0 * (double)iters * 8.0 * 512.0;   // 8x8x4 FMAs = 512 flops per warp-level DMMA
+    return fp64_probe_launch(ctas, iters, sink, static_cast<cudaStream_t>(stream));
 }
 
 int dlsa_irls_tiled_schedule(int px, int fit_intercept, uint32_t* sched_out, int* info) {

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
         // chunk from global to shared memory
         auto load_pre = [&](const double* src, int ci) -> double {
             const int64_t r = (c_lo + ci) * kTCH + row;
-            return (ci < my_n && r < n_k) ? __ldg(src + row_lo + r) : 0.0;
+            return (ci < my_n && r < n_k) ? __ldg(src + (row_lo - a.part_off[0]) + r) : 0.0;
         };
         double y_next = PRE ? 0.0 : load_y(lw);
         double w_next = PRE ? load_pre(a.pre_w, lw) : 0.0, r_next = PRE ? load_pre(a.pre_r, lw) : 0.0;
@@ -300,6 +300,13 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
                 wv = 1.0;
                 rv = yv;
                 if (rowvalid) llacc = fma(yv, yv, llacc);
+                // The linear body does not scale its A fragments by w, so the rows past `valid` of a tail chunk (what an
+                // earlier chunk left in this stage) must not stay: blank them before the MMA warps are released.
+                if (valid < kTCH) {
+                    double* stale = tiles + (size_t)st * stage_doubles + (size_t)valid * Sd;
+                    for (int e = lane; e < (kTCH - valid) * Sd; e += 32) stale[e] = 0.0;
+                    fence_proxy_async();
+                }
             }
             if (act) {
                 ws_all[st * kTCH + row] = rowvalid ? wv : 0.0;
@@ -438,7 +445,7 @@ __global__ void slice_reduce_tiled_kernel(const double* __restrict__ pH, const d
 
 // The link stage as its own streaming kernel (PRE mode, used when the Gram needs sibling CTAs or p is large): for every
 // row eta = x'beta_k, prob = sigmoid(eta), w = prob(1-prob), r = y - prob and the log-likelihood term, written to
-// w[n], r[n], ll[n] (global row index).  With TG sibling CTAs per partition slice the fused link stage is computed TG
+// w[n], r[n], ll[n] (row index relative to part_off[0]: the caller may pass a window of a longer offsets array).  With TG sibling CTAs per partition slice the fused link stage is computed TG
 // times over, by 3 warps per CTA whose FP64 instructions queue behind 12 DMMA streams (~100 cycles each, measured): at
 // p = 500 that is slower than reading X a second time at HBM speed.  One warp takes 32 rows: 8 batches of 4 rows with
 // lane = column stripe (coalesced), a transposed butterfly per batch, then ONE sigmoid per lane for the 32 rows.
@@ -465,6 +472,11 @@ __global__ void __launch_bounds__(kLinkWarps * 32) tiled_link_kernel(const doubl
     const int64_t row_lo = part_off[k];
     const int64_t n_k = part_off[k + 1] - row_lo;
     const double* Xp = X + row_lo * ldx;
+    y += row_lo;
+    const int64_t out_lo = row_lo - part_off[0];
+    wout += out_lo;
+    rout += out_lo;
+    if (llout != nullptr) llout += out_lo;
     for (int64_t base = ((int64_t)blockIdx.x * kLinkWarps + warp) * 32; base < n_k;
          base += (int64_t)gridDim.x * kLinkWarps * 32) {
 #pragma unroll 1
@@ -501,18 +513,18 @@ __global__ void __launch_bounds__(kLinkWarps * 32) tiled_link_kernel(const doubl
         const int64_t r = base + lane;
         if (r < n_k) {
             const double eta = eta_s[warp * 32 + lane] + b0;
-            const double yv = __ldg(y + row_lo + r);
+            const double yv = __ldg(y + r);
             if (poisson) {
                 const double mu = exp_clamped(eta);
-                wout[row_lo + r] = mu;
-                rout[row_lo + r] = yv - mu;
-                if (llout != nullptr) llout[row_lo + r] = fma(yv, eta, -mu);
+                wout[r] = mu;
+                rout[r] = yv - mu;
+                if (llout != nullptr) llout[r] = fma(yv, eta, -mu);
             } else {
                 const double e = exp_nonpos(-fabs(eta));
                 const double pr = div_pos((eta >= 0.0) ? 1.0 : e, 1.0 + e);
-                wout[row_lo + r] = pr * (1.0 - pr);
-                rout[row_lo + r] = yv - pr;
-                if (llout != nullptr) llout[row_lo + r] = yv * eta - (fmax(eta, 0.0) + log1p_01(e));
+                wout[r] = pr * (1.0 - pr);
+                rout[r] = yv - pr;
+                if (llout != nullptr) llout[r] = yv * eta - (fmax(eta, 0.0) + log1p_01(e));
             }
         }
         __syncwarp();

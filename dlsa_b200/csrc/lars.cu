@@ -534,7 +534,7 @@ int lars_launch(const double* Sigma0, const double* b0, int p0, int intercept, d
                  "lars: workspace too small");
     LarsArgs a;
     a.Sigma0 = Sigma0; a.b0 = b0; a.p0 = p0; a.intercept = intercept ? 1 : 0; a.type = type;
-    a.max_steps = max_steps > 0 ? max_steps : 8 * m;
+    a.max_steps = max_steps >= 0 ? max_steps : 8 * m;  // 0 steps = the zero row only, as the reference's loop (dlsa/lsa.py:126)
     a.n = n; a.eps = eps;
     a.beta_path = beta_path; a.beta0_path = beta0_path; a.rss = rss; a.aic = aic; a.bic = bic; a.dof = dof; a.info = info;
     double* ws = static_cast<double*>(workspace);

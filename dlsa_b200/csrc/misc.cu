@@ -55,6 +55,87 @@ int simulate_launch(double* X, int64_t ldx, double* y, int64_t row0, int64_t n, 
     return check_launch("simulate_kernel");
 }
 
+// ---- FP64 peak probe: what this GPU's DMMA pipe delivers right now (the roofline denominator bench.py reports) ------
+// 16 warps per SM, 8 independent DMMA.8x8x4 accumulator chains per warp, registers only.
+__global__ void __launch_bounds__(512, 1) fp64_probe_kernel(double* __restrict__ sink, int iters) {
+    double c0[8], c1[8];
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c0[i] = 0.0; c1[i] = 0.0; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) dmma884(c0[i], c1[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c0[i] + c1[i];
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int fp64_probe_launch(int ctas, int iters, double* sink, cudaStream_t st) {
+    fp64_probe_kernel<<<ctas, 512, 0, st>>>(sink, iters);
+    count_launch();
+    return check_launch("fp64_probe_kernel");
+}
+
+// ---- airline-shaped compact design (BASELINE.json configs[2]), counter-based like simulate_kernel ----------------
+// One thread per row: n_num numerics ~ N(0,1) (columns 0..n_num-1 of the counter space), one uniform per categorical
+// column (column 1000 + c) pushed through that column's cumulative level shares (level 0 = baseline -> code -1), the
+// label from the row's linear predictor (column 0xFFFFFFFF).  Rows depend on (seed, global row) only, so any sharding
+// of the rows over GPUs sees the same data.
+struct AirlineArgs {
+    double* numeric; int64_t ldn; int* codes; double* y;
+    int64_t row0, n;
+    int n_num, n_cat;
+    const int* levels;      // [n_cat] levels per column INCLUDING the baseline
+    const double* cdf;      // concatenated cumulative shares, levels[c] entries per column
+    const double* beta_num; // [n_num]
+    const double* beta_lev; // concatenated, levels[c]-1 entries per column (non-baseline levels)
+    double beta0;
+    uint64_t seed;
+};
+__global__ void __launch_bounds__(256) airline_kernel(const AirlineArgs a) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t grow = (uint64_t)(a.row0 + r);
+        double eta = a.beta0;
+        for (int c = 0; c < a.n_num; c++) {
+            const double v = gauss(a.seed, grow, (uint64_t)c);
+            a.numeric[r * a.ldn + c] = v;
+            eta = fma(v, a.beta_num[c], eta);
+        }
+        int cb = 0, lb = 0;
+        for (int c = 0; c < a.n_cat; c++) {
+            const int L = a.levels[c];
+            const double u = u01(a.seed, grow, 1000ULL + (uint64_t)c);
+            int lo = 0, hi = L - 1;        // first level whose cumulative share exceeds u (searchsorted, side = right)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (u < a.cdf[cb + mid]) hi = mid; else lo = mid + 1;
+            }
+            a.codes[r * a.n_cat + c] = lo - 1;
+            if (lo > 0) eta += a.beta_lev[lb + lo - 1];
+            cb += L;
+            lb += L - 1;
+        }
+        const double u = u01(a.seed, grow, 0xFFFFFFFFULL);
+        a.y[r] = (u < sigmoid_f64(eta)) ? 1.0 : 0.0;
+    }
+}
+
+int airline_launch(double* numeric, int64_t ldn, int* codes, double* y, int64_t row0, int64_t n, int n_num, int n_cat,
+                   const int* levels, const double* cdf, double beta0, const double* beta_num, const double* beta_lev,
+                   uint64_t seed, cudaStream_t st) {
+    if (n == 0) return 0;
+    AirlineArgs a;
+    a.numeric = numeric; a.ldn = ldn; a.codes = codes; a.y = y; a.row0 = row0; a.n = n; a.n_num = n_num; a.n_cat = n_cat;
+    a.levels = levels; a.cdf = cdf; a.beta_num = beta_num; a.beta_lev = beta_lev; a.beta0 = beta0; a.seed = seed;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    airline_kernel<<<(int)blocks, 256, 0, st>>>(a);
+    count_launch();
+    return check_launch("airline_kernel");
+}
+
 // ---- f1: per-partition log-likelihood of q coefficient vectors (dlsa/models.py:216-222) -------------------
 // y log(prob) + (1-y) log(1-prob) == y*eta - log(1+exp(eta)), evaluated in the overflow-free form.
 constexpr int kEvalMaxQ = 8;

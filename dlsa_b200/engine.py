@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
-from typing import Optional
+from typing import Callable, Optional
 
 import torch
 
@@ -57,6 +57,9 @@ class PartitionFits:
     pilot_passes: int = 0       # passes over the pilot block only (pooled warm start), 0 when cold-started
     pilot_partitions: int = 0
     cold_restart: bool = False  # the warm-started fit left a partition unconverged and the batch was refitted from 0
+    # deferred validation (dlsa_fit reads every scalar the host needs in ONE device->host copy at the end of the step)
+    n_bad: Optional[torch.Tensor] = None        # [1] int32 on the device: partitions whose status is not ST_OK
+    cold_refit: Optional[Callable[[], "PartitionFits"]] = None   # set when the fit was warm-started and not yet checked
 
 
 @dataclasses.dataclass
@@ -206,7 +209,7 @@ def _newton_fit(pass_fn, K: int, p: int, dev, cfg: EngineConfig, n_rows: int, be
     check(lib.dlsa_batched_symv_f64(H.data_ptr(), beta.data_ptr(), K, p, Hb.data_ptr(), _stream()),
           "dlsa_batched_symv_f64")
     return PartitionFits(coef=beta, Sig_inv=H, Sig_invMcoef=Hb, status=status, iters=iters, loglik=ll, passes=passes,
-                         n_rows=n_rows)
+                         n_rows=n_rows, n_bad=(status != _lib.ST_OK).sum(dtype=torch.int32).view(1))
 
 
 def _pooled_start(pilot: PartitionFits) -> Optional[torch.Tensor]:
@@ -219,10 +222,12 @@ def _pooled_start(pilot: PartitionFits) -> Optional[torch.Tensor]:
 
 
 def _fit_warm(make_pass, part_offsets, K: int, p: int, dev, cfg: EngineConfig, n_rows: int, beta_init,
-              pooled_start=None) -> PartitionFits:
+              pooled_start=None, defer_check: bool = False) -> PartitionFits:
     """Cold or pooled-warm-start Newton fit (EngineConfig.warm_start).  ``make_pass(offsets)`` returns the pass_fn over
     the partitions ``offsets`` names (a prefix view of ``part_offsets`` for the pilot block: same X, same rows).
-    ``pooled_start`` [p]: a pooled coefficient vector from an earlier block of the same job (no pilot needed)."""
+    ``pooled_start`` [p]: a pooled coefficient vector from an earlier block of the same job (no pilot needed).
+    ``defer_check``: do not read the warm-started fit's status here (a host round trip); the caller reads ``n_bad`` with
+    its other scalars and calls ``cold_refit()`` if it is non-zero."""
     pilot_passes = Kp = 0
     warm = False
     if beta_init is None and pooled_start is not None and cfg.warm_start:
@@ -241,18 +246,26 @@ def _fit_warm(make_pass, part_offsets, K: int, p: int, dev, cfg: EngineConfig, n
             warm = True
     fits = _newton_fit(make_pass(part_offsets), K, p, dev, cfg, n_rows, beta_init)
     fits.pilot_passes, fits.pilot_partitions = pilot_passes, Kp
-    if warm and bool((fits.status != _lib.ST_OK).any().item()):
-        cold = _newton_fit(make_pass(part_offsets), K, p, dev, cfg, n_rows, None)
-        cold.passes += fits.passes
-        cold.pilot_passes, cold.pilot_partitions, cold.cold_restart = pilot_passes, Kp, True
-        fits = cold
+    if warm:
+        warm_passes = fits.passes
+
+        def cold_refit() -> PartitionFits:
+            cold = _newton_fit(make_pass(part_offsets), K, p, dev, cfg, n_rows, None)
+            cold.passes += warm_passes
+            cold.pilot_passes, cold.pilot_partitions, cold.cold_restart = pilot_passes, Kp, True
+            return cold
+
+        if defer_check:
+            fits.cold_refit = cold_refit
+        elif int(fits.n_bad.item()) != 0:
+            fits = cold_refit()
     return fits
 
 
 def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor, fit_intercept: bool = False,
                             config: Optional[EngineConfig] = None, beta_init: Optional[torch.Tensor] = None,
-                            pooled_start: Optional[torch.Tensor] = None, family: int = _lib.FAMILY_LOGISTIC
-                            ) -> PartitionFits:
+                            pooled_start: Optional[torch.Tensor] = None, family: int = _lib.FAMILY_LOGISTIC,
+                            defer_check: bool = False, max_part_rows: Optional[int] = None) -> PartitionFits:
     """Per-partition logistic MLE for every partition at once (the map side, dlsa/models.py:42-147).
 
     X [n, px] float64 row-major on the GPU with each partition's rows contiguous; ``part_offsets`` int64 [K+1].
@@ -265,8 +278,10 @@ def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torc
     K = part_offsets.numel() - 1
     px = X.shape[1]
     p = px + (1 if fit_intercept else 0)
-    sizes = part_offsets[1:] - part_offsets[:-1]
-    max_rows = int(sizes.max().item()) if K > 0 else 0
+    if max_part_rows is None:  # one host round trip; callers that know the largest partition pass it in
+        sizes = part_offsets[1:] - part_offsets[:-1]
+        max_part_rows = int(sizes.max().item()) if K > 0 else 0
+    max_rows = int(max_part_rows)
 
     def make_pass(offsets):
         ws_pass = _workspace(lib.dlsa_irls_pass_workspace_bytes(offsets.numel() - 1, p, max_rows), dev)
@@ -276,7 +291,7 @@ def fit_logistic_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torc
                       want_loglik=want_ll, out=out, workspace=ws_pass, full=full)
         return pass_fn
 
-    return _fit_warm(make_pass, part_offsets, K, p, dev, cfg, int(X.shape[0]), beta_init, pooled_start)
+    return _fit_warm(make_pass, part_offsets, K, p, dev, cfg, int(X.shape[0]), beta_init, pooled_start, defer_check)
 
 
 def fit_poisson_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor, fit_intercept: bool = False,
@@ -353,7 +368,8 @@ def cat_supported(n_num: int, n_levels) -> bool:
 
 def fit_logistic_partitions_cat(numeric, codes, n_levels, y, part_offsets, fit_intercept: bool = False, mean=None,
                                 std=None, config: Optional[EngineConfig] = None,
-                                beta_init: Optional[torch.Tensor] = None) -> PartitionFits:
+                                beta_init: Optional[torch.Tensor] = None, pooled_start: Optional[torch.Tensor] = None,
+                                defer_check: bool = False, max_part_rows: Optional[int] = None) -> PartitionFits:
     """``fit_logistic_partitions`` for a design with dummy blocks kept compact: numeric [n, n_num] float64 (optionally
     standardised on load with mean/std, dlsa/models.py:99-101) and codes [n, n_cat] int32.  Same outputs, same column
     order as fitting the one-hot expanded matrix (the dummy branch of logistic_model, dlsa/models.py:56-91)."""
@@ -361,8 +377,10 @@ def fit_logistic_partitions_cat(numeric, codes, n_levels, y, part_offsets, fit_i
     dev, y, n_levels, n_num = _check_cat_inputs(numeric, codes, n_levels, y, part_offsets)
     K = part_offsets.numel() - 1
     p = int(fit_intercept) + n_num + sum(n_levels)
-    sizes = part_offsets[1:] - part_offsets[:-1]
-    max_rows = int(sizes.max().item()) if K > 0 else 0
+    if max_part_rows is None:
+        sizes = part_offsets[1:] - part_offsets[:-1]
+        max_part_rows = int(sizes.max().item()) if K > 0 else 0
+    max_rows = int(max_part_rows)
     import ctypes as C
     nl = (C.c_int * len(n_levels))(*n_levels)
     if mean is not None:
@@ -378,18 +396,24 @@ def fit_logistic_partitions_cat(numeric, codes, n_levels, y, part_offsets, fit_i
                           want_loglik=want_ll, out=out, workspace=ws_pass, full=full)
         return pass_fn
 
-    return _fit_warm(make_pass, part_offsets, K, p, dev, cfg, int(codes.shape[0]), beta_init)
+    return _fit_warm(make_pass, part_offsets, K, p, dev, cfg, int(codes.shape[0]), beta_init, pooled_start, defer_check)
 
 
-def fit_linear_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor) -> PartitionFits:
+def fit_linear_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.Tensor,
+                          max_part_rows: Optional[int] = None, events=None) -> PartitionFits:
     """Per-partition OLS in closed form (R ``lm(y~x-1)`` + ``solve(vcov)``, dlsa/R/wlse_func.R:169-182):
-    one fused pass gives X'X, X'y, y'y (K8); theta_k by batched Cholesky; Sig_inv_k = X'X / sigma2_k."""
+    one fused pass gives X'X, X'y, y'y (K8); theta_k by batched Cholesky; Sig_inv_k = X'X / sigma2_k.
+    ``events``: optional (event,) recorded right after the fused pass (bench.py's per-kernel bracket)."""
     dev, y = _check_inputs(X, y, part_offsets)
     K = part_offsets.numel() - 1
     p = X.shape[1]
-    sizes = part_offsets[1:] - part_offsets[:-1]
-    max_rows = int(sizes.max().item()) if K > 0 else 0
+    if max_part_rows is None:
+        sizes = part_offsets[1:] - part_offsets[:-1]
+        max_part_rows = int(sizes.max().item()) if K > 0 else 0
+    max_rows = int(max_part_rows)
     g, H, yty = irls_pass(X, y, part_offsets, None, False, _lib.FAMILY_LINEAR, None, max_rows, want_loglik=True)
+    if events:
+        events[0].record()
     theta = torch.empty(K, p, dtype=_F64, device=dev)
     status = torch.zeros(K, dtype=torch.int32, device=dev)
     ws = _workspace(lib.dlsa_newton_update_workspace_bytes(K, p), dev)
@@ -400,39 +424,94 @@ def fit_linear_partitions(X: torch.Tensor, y: torch.Tensor, part_offsets: torch.
                                  part_offsets.data_ptr(), K, p, sigma2.data_ptr(), _stream()), "dlsa_ols_scale_f64")
     return PartitionFits(coef=theta, Sig_inv=H, Sig_invMcoef=g, status=status,
                          iters=torch.ones(K, dtype=torch.int32, device=dev), loglik=sigma2, passes=1,
-                         n_rows=int(X.shape[0]))
+                         n_rows=int(X.shape[0]), n_bad=(status != _lib.ST_OK).sum(dtype=torch.int32).view(1))
+
+
+def reduce_partitions(fits: PartitionFits) -> torch.Tensor:
+    """K4: fixed-order sum over this rank's partitions into the packed buffer
+    [sum Sig_inv (p*p) | sum Sig_inv coef (p) | sum coef (p) | K_eff | K] — the allreduce payload (parallel.py)."""
+    K, p = fits.coef.shape
+    packed = torch.empty(parallel.packed_len(p), dtype=_F64, device=fits.coef.device)
+    check(lib.dlsa_partition_reduce_f64(fits.Sig_inv.data_ptr(), fits.Sig_invMcoef.data_ptr(), fits.coef.data_ptr(),
+                                        fits.status.data_ptr(), K, p, packed.data_ptr(), _stream()),
+          "dlsa_partition_reduce_f64")
+    return packed
+
+
+class _PendingCombine:
+    """K5 queued on the stream; ``meta`` [3] float64 on the device = (K_eff, K_total, solve status), read by finish()."""
+
+    def __init__(self, packed, p, theta, st, num_partitions):
+        self.packed, self.p, self.theta, self.num_partitions = packed, p, theta, num_partitions
+        self.meta = torch.cat([packed[p * p + 2 * p:], st.to(_F64)])
+
+    def finish(self, meta_host) -> CombineResult:
+        K_eff, K_total, st = int(round(meta_host[0])), int(round(meta_host[1])), int(round(meta_host[2]))
+        if K_eff == 0:
+            raise Exception("Zero-length grouped pandas DataFrame obtained, check the input.")  # dlsa/dlsa.py:36-39
+        p = self.p
+        S = self.packed[: p * p].view(p, p)
+        v = self.packed[p * p: p * p + p]
+        c = self.packed[p * p + p: p * p + 2 * p]
+        theta = self.theta
+        if st != _lib.ST_OK:
+            # dlsa/dlsa.py:48 is np.linalg.lstsq: the minimum-norm solution when the sum is singular.  Rare (collinear
+            # dummies, an empty level), off the hot path: SVD pseudo-inverse of the p x p sum through torch.linalg.
+            U, sv, Vh = torch.linalg.svd(S)
+            cut = torch.finfo(_F64).eps * p * sv.max()   # numpy's default rcond = eps * max(M, N)
+            inv = torch.where(sv > cut, 1.0 / sv, torch.zeros_like(sv))
+            theta = Vh.T @ (inv * (U.T @ v))
+        Kd = K_total if self.num_partitions is None else self.num_partitions
+        return CombineResult(beta_byOLS=theta, beta_byONESHOT=c / Kd, Sig_inv_sum=S.clone(), K_eff=K_eff,
+                             K_total=K_total)
+
+
+def _queue_combine(packed: torch.Tensor, p: int, group=None, num_partitions: Optional[int] = None,
+                   allreduce: bool = True) -> _PendingCombine:
+    dev = packed.device
+    if allreduce:
+        parallel.allreduce_packed(packed, group)  # the one collective of the whole algorithm
+    theta = torch.empty(p, dtype=_F64, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _workspace(lib.dlsa_newton_update_workspace_bytes(1, p), dev)
+    check(lib.dlsa_spd_solve_f64(packed.data_ptr(), packed[p * p:].data_ptr(), 1, p, theta.data_ptr(), st.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), _stream()), "dlsa_spd_solve_f64")
+    return _PendingCombine(packed, p, theta, st, num_partitions)
+
+
+def combine_packed(packed: torch.Tensor, p: int, group=None, num_partitions: Optional[int] = None,
+                   allreduce: bool = True) -> CombineResult:
+    """ONE allreduce of the packed buffer when torch.distributed is initialised, then K5 (Cholesky solve of the SPD
+    sum; the reference's lstsq, dlsa/dlsa.py:48, whose minimum-norm answer is reproduced when the sum is singular)."""
+    pend = _queue_combine(packed, p, group, num_partitions, allreduce)
+    return pend.finish(pend.meta.tolist())
 
 
 def combine_partitions(fits: PartitionFits, group=None, num_partitions: Optional[int] = None) -> CombineResult:
     """One-round combine (dlsa_mapred, dlsa/dlsa.py:21-61): K4 fixed-order local sum, ONE allreduce of the packed
-    [sum Sig_inv | sum Sig_inv coef | sum coef | K_eff | K] buffer when torch.distributed is initialised, then K5
-    (Cholesky solve of the SPD sum — the reference's lstsq, :48).  beta_byONESHOT = sum coef / K (:51-52), with K
-    the total partition count (skipped partitions count, as getNumPartitions() does)."""
-    K, p = fits.coef.shape
-    dev = fits.coef.device
-    packed = torch.empty(p * p + 2 * p + 2, dtype=_F64, device=dev)
-    check(lib.dlsa_partition_reduce_f64(fits.Sig_inv.data_ptr(), fits.Sig_invMcoef.data_ptr(), fits.coef.data_ptr(),
-                                        fits.status.data_ptr(), K, p, packed.data_ptr(), _stream()),
-          "dlsa_partition_reduce_f64")
-    parallel.allreduce_packed(packed, group)  # the one collective of the whole algorithm
-    S, v, c, K_eff, K_total = parallel.unpack(packed, p)
-    if K_eff == 0:
-        raise Exception("Zero-length grouped pandas DataFrame obtained, check the input.")  # dlsa/dlsa.py:36-39
-    theta = torch.empty(p, dtype=_F64, device=dev)
-    st = torch.zeros(1, dtype=torch.int32, device=dev)
-    ws = _workspace(lib.dlsa_newton_update_workspace_bytes(1, p), dev)
-    check(lib.dlsa_spd_solve_f64(S.data_ptr(), v.data_ptr(), 1, p, theta.data_ptr(), st.data_ptr(), ws.data_ptr(),
-                                 ws.numel(), _stream()), "dlsa_spd_solve_f64")
-    if int(st.item()) != _lib.ST_OK:
-        raise _lib.DlsaLibraryError("combined Sig_inv is not positive definite; DLSA needs an SPD sum "
-                                    "(the reference's lstsq min-norm fallback is not provided)")
-    Kd = K_total if num_partitions is None else num_partitions
-    return CombineResult(beta_byOLS=theta, beta_byONESHOT=c / Kd, Sig_inv_sum=S.clone(), K_eff=K_eff, K_total=K_total)
+    [sum Sig_inv | sum Sig_inv coef | sum coef | K_eff | K] buffer when torch.distributed is initialised, then K5.
+    beta_byONESHOT = sum coef / K (:51-52), with K the total partition count (skipped partitions count, as
+    getNumPartitions() does)."""
+    return combine_packed(reduce_partitions(fits), fits.coef.shape[1], group, num_partitions)
 
 
-def lars_path(Sigma0: torch.Tensor, b0: torch.Tensor, intercept: bool, n: float, type: str = "lar",
-              eps: float = 2.220446049250313e-16, max_steps: Optional[int] = None) -> LarsResult:
-    """lars_lsa on the device (K6 + K7): dlsa/lsa.py:90-212; intercept branch per the R original."""
+class _PendingLars:
+    """K6/K7 queued on the stream; ``info`` [4] int32 on the device = (rows, argmin AIC, argmin BIC, error)."""
+
+    def __init__(self, bufs, info):
+        self.bufs, self.info = bufs, info
+
+    def finish(self, info_host) -> LarsResult:
+        nrows, ia, ib, err = (int(round(v)) for v in info_host)
+        if err:
+            raise _lib.DlsaLibraryError("lars path: no variable could enter (singular Sigma)")
+        beta, beta0, rss, aic, bic, dof = self.bufs
+        return LarsResult(AIC=aic[:nrows], BIC=bic[:nrows], beta=beta[:nrows], beta0=beta0[:nrows], RSS=rss[:nrows],
+                          dof=dof[:nrows], argmin_AIC=ia, argmin_BIC=ib)
+
+
+def _queue_lars(Sigma0: torch.Tensor, b0: torch.Tensor, intercept: bool, n: float, type: str = "lar",
+                eps: float = 2.220446049250313e-16, max_steps: Optional[int] = None) -> _PendingLars:
     dev = _require_cuda(Sigma0, b0)
     Sigma0 = Sigma0.to(_F64).contiguous()
     b0 = b0.to(_F64).contiguous().view(-1)
@@ -442,7 +521,7 @@ def lars_path(Sigma0: torch.Tensor, b0: torch.Tensor, intercept: bool, n: float,
     if type not in ("lar", "lasso"):
         raise ValueError("type must be 'lar' or 'lasso'")
     m = p0 - (1 if intercept else 0)
-    steps = 8 * m if max_steps is None else int(max_steps)
+    steps = 8 * m if (max_steps is None or int(max_steps) < 0) else int(max_steps)  # 0: the zero row only (dlsa/lsa.py:126)
     rows = steps + 1
     beta = torch.zeros(rows, m, dtype=_F64, device=dev)
     beta0 = torch.zeros(rows, dtype=_F64, device=dev)
@@ -457,11 +536,14 @@ def lars_path(Sigma0: torch.Tensor, b0: torch.Tensor, intercept: bool, n: float,
                                  beta.data_ptr(), beta0.data_ptr(), rss.data_ptr(), aic.data_ptr(), bic.data_ptr(),
                                  dof.data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
           "dlsa_lars_path_f64")
-    nrows, ia, ib, err = info.tolist()
-    if err:
-        raise _lib.DlsaLibraryError("lars path: no variable could enter (singular Sigma)")
-    return LarsResult(AIC=aic[:nrows], BIC=bic[:nrows], beta=beta[:nrows], beta0=beta0[:nrows], RSS=rss[:nrows],
-                      dof=dof[:nrows], argmin_AIC=ia, argmin_BIC=ib)
+    return _PendingLars((beta, beta0, rss, aic, bic, dof), info)
+
+
+def lars_path(Sigma0: torch.Tensor, b0: torch.Tensor, intercept: bool, n: float, type: str = "lar",
+              eps: float = 2.220446049250313e-16, max_steps: Optional[int] = None) -> LarsResult:
+    """lars_lsa on the device (K6 + K7): dlsa/lsa.py:90-212; intercept branch per the R original."""
+    pend = _queue_lars(Sigma0, b0, intercept, n, type, eps, max_steps)
+    return pend.finish(pend.info.tolist())
 
 
 def logistic_loglik(X, y, part_offsets, par, fit_intercept=False) -> torch.Tensor:
@@ -494,27 +576,58 @@ def column_stats(X: torch.Tensor) -> torch.Tensor:
     return stats
 
 
+def _global_rows(n_local: int, dev, group=None) -> float:
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        n = torch.tensor([float(n_local)], dtype=_F64, device=dev)
+        dist.all_reduce(n, group=group)
+        return float(n.item())
+    return float(n_local)
+
+
+def finish_fit(fits: PartitionFits, fit_intercept: bool, sample_size: float, type: str = "lar", group=None,
+               num_partitions: Optional[int] = None, packed: Optional[torch.Tensor] = None):
+    """Reduce side of the hot path after the map: K4 -> ONE allreduce -> K5 -> K6/K7, all queued on the stream without
+    a host round trip; every scalar the host needs (warm-start failures, K_eff, solve status, path length, argmins) comes
+    back in ONE device->host copy.  ``fits.cold_refit`` (set by a deferred warm-started fit) is honoured: if any
+    partition did not reach ST_OK the batch is refitted from beta = 0 and the reduce side runs again.  ``packed``: a
+    pre-reduced local buffer (chunked maps accumulate it themselves).  Returns (fits, comb, path)."""
+    p = fits.coef.shape[1]
+    local = reduce_partitions(fits) if packed is None else packed
+    pc = _queue_combine(local, p, group, num_partitions)
+    pl = _queue_lars(local[: p * p].view(p, p), pc.theta, fit_intercept, sample_size, type=type)
+    n_bad = fits.n_bad if fits.n_bad is not None else torch.zeros(1, dtype=torch.int32, device=local.device)
+    meta = torch.cat([n_bad.to(_F64), pc.meta, pl.info.to(_F64)]).tolist()   # the step's one host round trip
+    if fits.cold_refit is not None and meta[0] != 0 and packed is None:
+        cold = fits.cold_refit()
+        return finish_fit(cold, fit_intercept, sample_size, type, group, num_partitions)
+    fits.cold_refit = None
+    comb = pc.finish(meta[1:4])
+    if int(round(meta[3])) != _lib.ST_OK:   # singular sum: the path must follow the lstsq estimate, not the failed solve
+        path = lars_path(comb.Sig_inv_sum, comb.beta_byOLS, fit_intercept, sample_size, type=type)
+    else:
+        path = pl.finish(meta[4:8])
+    return fits, comb, path
+
+
 def dlsa_fit(X, y, part_offsets, fit_intercept=False, sample_size=None, type="lar", config=None, group=None,
-             family="logistic"):
+             family="logistic", max_part_rows=None):
     """Whole hot path on this rank's partitions: map (fit) -> combine (+allreduce) -> LARS + AIC/BIC.
-    ``sample_size`` is the global n used by BIC (defaults to the all-rank row count)."""
+    ``sample_size`` is the global n used by BIC (defaults to the all-rank row count).  After the Newton loop (whose
+    convergence counter the host reads one iteration late) the step makes ONE host round trip (``finish_fit``)."""
+    if sample_size is None:
+        sample_size = _global_rows(int(X.shape[0]), X.device, group)
     if family == "logistic":
-        fits = fit_logistic_partitions(X, y, part_offsets, fit_intercept, config)
+        fits = fit_logistic_partitions(X, y, part_offsets, fit_intercept, config, defer_check=True,
+                                       max_part_rows=max_part_rows)
     elif family == "linear":
         fits = fit_linear_partitions(X, y, part_offsets)
     elif family == "poisson":
-        fits = fit_poisson_partitions(X, y, part_offsets, fit_intercept, config)
+        fits = fit_logistic_partitions(X, y, part_offsets, fit_intercept, config, None, None, _lib.FAMILY_POISSON,
+                                       defer_check=True, max_part_rows=max_part_rows)
     else:
         raise ValueError("family must be 'logistic', 'linear' or 'poisson'")
-    comb = combine_partitions(fits, group=group)
-    if sample_size is None:
-        n = torch.tensor([float(X.shape[0])], dtype=_F64, device=X.device)
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(n, group=group)
-        sample_size = float(n.item())
-    path = lars_path(comb.Sig_inv_sum, comb.beta_byOLS, fit_intercept, sample_size, type=type)
-    return fits, comb, path
+    return finish_fit(fits, fit_intercept, float(sample_size), type, group)
 
 
 def dlsa_fit_host(Xh: torch.Tensor, yh: torch.Tensor, part_offsets_host: torch.Tensor, fit_intercept=False,
@@ -572,13 +685,72 @@ def dlsa_fit_host(Xh: torch.Tensor, yh: torch.Tensor, part_offsets_host: torch.T
                          loglik=None if parts[0].loglik is None else torch.cat([f.loglik for f in parts]),
                          passes=max(f.passes for f in parts), n_rows=int(n),
                          pilot_passes=parts[0].pilot_passes, pilot_partitions=parts[0].pilot_partitions,
-                         cold_restart=any(f.cold_restart for f in parts))
-    comb = combine_partitions(fits, group=group)
+                         cold_restart=any(f.cold_restart for f in parts),
+                         n_bad=torch.stack([f.n_bad for f in parts]).sum(0).to(torch.int32))
     if sample_size is None:
-        nt = torch.tensor([float(n)], dtype=_F64, device=dev)
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(nt, group=group)
-        sample_size = float(nt.item())
-    path = lars_path(comb.Sig_inv_sum, comb.beta_byOLS, fit_intercept, sample_size, type=type)
-    return fits, comb, path
+        sample_size = _global_rows(int(n), dev, group)
+    return finish_fit(fits, fit_intercept, float(sample_size), type, group)
+
+
+def dlsa_fit_host_cat(numeric_h: torch.Tensor, codes_h: torch.Tensor, n_levels, yh: torch.Tensor,
+                      part_offsets_host: torch.Tensor, fit_intercept=True, mean=None, std=None, sample_size=None,
+                      type="lar", config=None, group=None, device=None, n_groups: int = 8, buffers=None):
+    """``dlsa_fit_host`` for the COMPACT categorical design: host-resident numeric [n, n_num] float64, codes [n, n_cat]
+    int32 (level index inside its block, -1 = baseline) and y [n] — 84 bytes per airline-shaped row instead of the 1456 of
+    the one-hot matrix, so the host->device copy shrinks 17x (what a Spark worker would hand over after StringIndexer,
+    dlsa/sdummies.py:95-116, or after dummies.select_dummy_factors).  Partition blocks are copied on a copy stream while
+    earlier blocks are fitted by the categorical fused pass K1c.  Returns (fits, comb, path)."""
+    for t in (numeric_h, codes_h, yh, part_offsets_host):
+        if t.device.type != "cpu":
+            raise ValueError("dlsa_fit_host_cat takes host tensors; use fit_logistic_partitions_cat for device data")
+    if numeric_h.dtype != _F64 or yh.dtype != _F64 or codes_h.dtype != torch.int32 or part_offsets_host.dtype != torch.int64:
+        raise TypeError("numeric, y must be float64, codes int32 and part_offsets int64")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    n = yh.numel()
+    K = part_offsets_host.numel() - 1
+    offs = part_offsets_host.tolist()
+    if buffers is None:
+        nd = torch.empty(numeric_h.shape, dtype=_F64, device=dev)
+        cd = torch.empty(codes_h.shape, dtype=torch.int32, device=dev)
+        yd = torch.empty(n, dtype=_F64, device=dev)
+    else:
+        nd, cd, yd = buffers
+    G = max(1, min(int(n_groups), K))
+    bounds = [(K * i) // G for i in range(G + 1)]
+    compute = torch.cuda.current_stream(dev)
+    copy = torch.cuda.Stream(dev)
+    copy.wait_stream(compute)
+    events = []
+    with torch.cuda.stream(copy):
+        for i in range(G):
+            r0, r1 = offs[bounds[i]], offs[bounds[i + 1]]
+            nd[r0:r1].copy_(numeric_h[r0:r1], non_blocking=True)
+            cd[r0:r1].copy_(codes_h[r0:r1], non_blocking=True)
+            yd[r0:r1].copy_(yh[r0:r1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            events.append(ev)
+    parts = []
+    pooled = None
+    for i in range(G):
+        k0, k1 = bounds[i], bounds[i + 1]
+        r0, r1 = offs[k0], offs[k1]
+        if k1 == k0:
+            continue
+        sizes_h = part_offsets_host[k0 + 1:k1 + 1] - part_offsets_host[k0:k1]
+        off_g = (part_offsets_host[k0:k1 + 1] - r0).to(dev, non_blocking=True)
+        compute.wait_event(events[i])
+        parts.append(fit_logistic_partitions_cat(nd[r0:r1], cd[r0:r1], n_levels, yd[r0:r1], off_g, fit_intercept, mean,
+                                                 std, config, pooled_start=pooled, max_part_rows=int(sizes_h.max())))
+        if pooled is None and len(parts) == 1 and G > 1:
+            pooled = _pooled_start(parts[0])
+    fits = PartitionFits(coef=torch.cat([f.coef for f in parts]), Sig_inv=torch.cat([f.Sig_inv for f in parts]),
+                         Sig_invMcoef=torch.cat([f.Sig_invMcoef for f in parts]),
+                         status=torch.cat([f.status for f in parts]), iters=torch.cat([f.iters for f in parts]),
+                         loglik=None, passes=max(f.passes for f in parts), n_rows=int(n),
+                         pilot_passes=parts[0].pilot_passes, pilot_partitions=parts[0].pilot_partitions,
+                         cold_restart=any(f.cold_restart for f in parts),
+                         n_bad=torch.stack([f.n_bad for f in parts]).sum(0).to(torch.int32))
+    if sample_size is None:
+        sample_size = _global_rows(int(n), dev, group)
+    return finish_fit(fits, fit_intercept, float(sample_size), type, group)

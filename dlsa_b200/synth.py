@@ -1,6 +1,6 @@
 """Synthetic data with the law of ``simulate_logistic`` (dlsa/models.py:6-40), generated on the device by a
 counter-based generator keyed by (seed, global row, column): any sharding of the rows over GPUs sees the same
-values.  ``host_uniform`` is the NumPy restatement of the device hash (bit-identical), used by the tests."""
+values.  The NumPy restatement of the device hash (bit-identical) is test infrastructure: ``oracle/synth_host.py``."""
 from __future__ import annotations
 
 import numpy as np
@@ -8,28 +8,8 @@ import torch
 
 from ._lib import lib, check
 
-_M1 = np.uint64(0xBF58476D1CE4E5B9)
-_M2 = np.uint64(0x94D049BB133111EB)
-_PHI = np.uint64(0x9E3779B97F4A7C15)
-_C2 = np.uint64(0xD1B54A32D192ED03)
-_C3 = np.uint64(0x8CB92BA72F3D8DD7)
-LABEL_COL = 0xFFFFFFFF
-
-
-def _mix64(z):
-    z = (z ^ (z >> np.uint64(30))) * _M1
-    z = (z ^ (z >> np.uint64(27))) * _M2
-    return z ^ (z >> np.uint64(31))
-
-
-def host_uniform(seed: int, rows: np.ndarray, cols: np.ndarray) -> np.ndarray:
-    """u01(seed, row, col) of csrc/misc.cu for broadcastable uint64 arrays rows, cols -> float64 in [0,1)."""
-    with np.errstate(over="ignore"):
-        rows = np.asarray(rows, dtype=np.uint64)
-        cols = np.asarray(cols, dtype=np.uint64)
-        z = _mix64(np.uint64(seed) + rows * _PHI)
-        z = _mix64(z + cols * _C2 + _C3)
-    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+LABEL_COL = 0xFFFFFFFF   # counter-space column of the label's uniform draw (csrc/misc.cu)
+CAT_COL0 = 1000          # counter-space column of categorical column 0 in the airline-shaped stream
 
 
 def true_beta(p: int) -> np.ndarray:
@@ -96,36 +76,34 @@ def airline_truth(seed: int = 11):
     return -1.0, b[:AIRLINE_NUM].copy(), b[AIRLINE_NUM:].copy()
 
 
-def airline_shaped_device(n: int, seed: int, device, chunk: int = 4_000_000):
-    """Compact airline-shaped design on ``device``: numeric [n,7] float64, codes [n,5] int32 (level-in-block index, -1 =
-    baseline level), n_levels (11,6,7,75,75), y [n] ~ Bernoulli(sigmoid(eta)).  torch's generator does the sampling
-    (benchmark input, not part of the hot path)."""
-    gen = torch.Generator(device=device)
-    gen.manual_seed(int(seed))
-    b0, bnum, blev = airline_truth()
-    bnum_d = torch.as_tensor(bnum, device=device)
-    n_levels = [L - 1 for L in AIRLINE_LEVELS]
-    base = np.concatenate([[0], np.cumsum(n_levels)])
-    blev_d = torch.as_tensor(np.concatenate([blev, [0.0]]), device=device)  # slot -1 -> 0 for the baseline level
-    numeric = torch.empty(n, AIRLINE_NUM, dtype=torch.float64, device=device)
-    codes = torch.empty(n, len(n_levels), dtype=torch.int32, device=device)
-    y = torch.empty(n, dtype=torch.float64, device=device)
-    cdfs = []
+def airline_cdfs():
+    """Cumulative level shares of the five categorical columns (uniform or Zipf(1)), level 0 = baseline."""
+    out = []
     for L, zipf in zip(AIRLINE_LEVELS, AIRLINE_ZIPF):
         w = 1.0 / np.arange(1, L + 1) if zipf else np.ones(L)
-        cdfs.append(torch.as_tensor(np.cumsum(w / w.sum()), device=device))
-    for s in range(0, n, chunk):
-        m = min(chunk, n - s)
-        num = torch.randn(m, AIRLINE_NUM, dtype=torch.float64, device=device, generator=gen)
-        eta = num @ bnum_d + b0
-        for c, cdf in enumerate(cdfs):
-            u = torch.rand(m, dtype=torch.float64, device=device, generator=gen)
-            lvl = torch.searchsorted(cdf, u).clamp_(max=AIRLINE_LEVELS[c] - 1)  # 0 = baseline (the most frequent level)
-            code = (lvl - 1).to(torch.int32)
-            codes[s:s + m, c] = code
-            idx = torch.where(code >= 0, code.to(torch.int64) + int(base[c]), torch.full_like(lvl, blev_d.numel() - 1))
-            eta += blev_d[idx]
-        u = torch.rand(m, dtype=torch.float64, device=device, generator=gen)
-        y[s:s + m] = (u < torch.sigmoid(eta)).to(torch.float64)
-        numeric[s:s + m] = num
+        out.append(np.cumsum(w / w.sum()))
+    return out
+
+
+def airline_shaped_device(n: int, seed: int, device, row0: int = 0, out=None):
+    """Rows [row0, row0+n) of the compact airline-shaped stream on ``device``: numeric [n,7] float64, codes [n,5] int32
+    (level-in-block index, -1 = baseline level), n_levels (11,6,7,75,75), y [n] ~ Bernoulli(sigmoid(eta)).  Counter-based
+    (``dlsa_simulate_airline_f64``): a row depends on (seed, global row index) only, so every sharding sees the same
+    data.  Benchmark / test input, not part of the hot path."""
+    b0, bnum, blev = airline_truth()
+    n_levels = [L - 1 for L in AIRLINE_LEVELS]
+    if out is None:
+        numeric = torch.empty(n, AIRLINE_NUM, dtype=torch.float64, device=device)
+        codes = torch.empty(n, len(n_levels), dtype=torch.int32, device=device)
+        y = torch.empty(n, dtype=torch.float64, device=device)
+    else:
+        numeric, codes, y = out
+    lev = torch.as_tensor(np.asarray(AIRLINE_LEVELS, dtype=np.int32), device=device)
+    cdf = torch.as_tensor(np.concatenate(airline_cdfs()), device=device)
+    bn = torch.as_tensor(bnum, device=device)
+    bl = torch.as_tensor(blev, device=device)
+    check(lib.dlsa_simulate_airline_f64(numeric.data_ptr(), numeric.stride(0), codes.data_ptr(), y.data_ptr(), int(row0),
+                                        int(n), AIRLINE_NUM, len(n_levels), lev.data_ptr(), cdf.data_ptr(), float(b0),
+                                        bn.data_ptr(), bl.data_ptr(), int(seed),
+                                        torch.cuda.current_stream().cuda_stream), "dlsa_simulate_airline_f64")
     return numeric, codes, n_levels, y

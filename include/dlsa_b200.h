@@ -150,7 +150,7 @@ int dlsa_partition_reduce_f64(const double *H, const double *Hbeta, const double
  * Replaces lars_lsa(Sigma0, b0, intercept, n, type, eps, max_steps)          dlsa/lsa.py:90-212
  *          (intercept branch as in the R original, dlsa/R/dlsa_alasso_func.R:115-125,243-245)
  *      and the first-argmin AIC/BIC selection of dlsa()                       dlsa/dlsa.py:90-91
- *   Sigma0 [p0,p0], b0 [p0]; m = p0 - (intercept?1:0); max_steps <= 0 means 8*m
+ *   Sigma0 [p0,p0], b0 [p0]; m = p0 - (intercept?1:0); max_steps < 0 means 8*m (0 = only the all-zero first row)
  *   beta_path [(max_steps+1), m], beta0_path/rss/aic/bic [(max_steps+1)], dof [(max_steps+1)] int
  *   info [4] int: {n_rows (= steps+1), argmin AIC, argmin BIC, error flag}
  */
@@ -178,6 +178,23 @@ int dlsa_logistic_loglik_f64(const double *X, int64_t ldx, const double *y, cons
  */
 int dlsa_simulate_f64(double *X, int64_t ldx, double *y, int64_t row0, int64_t n, int px, const double *beta_true,
                       uint64_t seed, int law, void *stream);
+
+/* Measurement aid (bench.py): a registers-only DMMA.8x8x4 stream, 16 warps per CTA, `ctas` CTAs (one per SM), `iters`
+ * x 8 independent MMAs per warp.  sink [ctas * 512] doubles; *flops_out (host) = floating-point operations the launch
+ * performs.  Timed with CUDA events it gives the FP64 tensor-pipe peak of THIS device at THIS moment — the roofline
+ * denominator of the fused pass (MEASURED_PEAKS.json carries no FP64 entry). */
+int dlsa_probe_fp64_dmma(int ctas, int iters, double *sink, double *flops_out, void *stream);
+
+/* Benchmark input for BASELINE.json configs[2] (airline-shaped data, SURVEY.md section 8d "C3"): the COMPACT design
+ *   numeric [n, ldn] (n_num columns ~ N(0,1)), codes [n, n_cat] int32 (level - 1; -1 = the baseline level 0), y [n],
+ *   rows [row0, row0 + n) of a counter-based stream keyed by (seed, global row), as dlsa_simulate_f64.
+ *   levels_dev [n_cat] = levels per column incl. the baseline; cdf_dev = their cumulative shares, concatenated;
+ *   eta = beta0 + numeric . beta_num + sum_c beta_lev[level_c]  (beta_lev: non-baseline levels, concatenated);
+ *   y ~ Bernoulli(sigmoid(eta)).  Stands in for the cleaned airline frame of projects/logistic_dlsa.py:213-237
+ *   after dummies.select_dummy_factors; it is input generation, not part of the timed path. */
+int dlsa_simulate_airline_f64(double *numeric, int64_t ldn, int *codes, double *y, int64_t row0, int64_t n, int n_num,
+                              int n_cat, const int *levels_dev, const double *cdf_dev, double beta0,
+                              const double *beta_num_dev, const double *beta_lev_dev, uint64_t seed, void *stream);
 
 /* a11  dense one-hot expansion with the layout of logistic_model's dummy branch (dlsa/models.py:56-79):
  *   X[i, col_base[c] + codes[i, c]] = 1 for every categorical column c whose code is >= 0

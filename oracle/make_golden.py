@@ -207,6 +207,75 @@ def golden_dummies():
     print("dummy frame", frame.shape, list(frame.columns)[:6], "zero-frame", zero.shape)
 
 
+def golden_eval():
+    """logistic_model_eval (dlsa/models.py:151-225) and logistic_model(..., data_info=...) (:99-101) run by the reference.
+
+    Cases: (a) no dummies, no intercept; (b) no dummies, intercept + standardisation; (c) a dummy column whose
+    get_dummies order coincides with the canonical (sorted) column order + intercept + standardisation.  The reference's
+    eval does not reindex the dummy design to the coefficient order (it multiplies by position, :216-219), so a design
+    whose get_dummies order differs from sorted order is evaluated against permuted coefficients — a reference defect;
+    case (c) is built so both orders agree and the value is well defined."""
+    out = {}
+    m = ref_shim.ref_models()
+    # (a), (b): simulated, p = 7, K = 3
+    df, X, y = sim_frame(6000, 7, 3, 3)
+    rng = np.random.default_rng(21)
+    names = ["x" + str(i) for i in range(7)]
+    par_a = pd.DataFrame(rng.standard_normal((7, 3)) * 0.5, columns=["beta_byOLS", "beta_byONESHOT", "beta_byBIC"])
+    par_b = pd.DataFrame(rng.standard_normal((8, 2)) * 0.5, columns=["beta_byOLS", "beta_byAIC"])
+    desc = df[names].describe()
+    data_info = {c: desc[c].to_numpy() for c in names}
+    ll_a, ll_b = [], []
+    for k in range(3):
+        part = df[df["partition_id"] == k].reset_index(drop=True)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ll_a.append(m.logistic_model_eval(part.copy(), "label", par_a).to_numpy().ravel())
+            ll_b.append(m.logistic_model_eval(part.copy(), "label", par_b, fit_intercept=True,
+                                              data_info=data_info).to_numpy().ravel())
+    out.update({"a_in_n": 6000, "a_in_p": 7, "a_in_K": 3, "a_in_seed": 3, "a_in_par": par_a.to_numpy(),
+                "a_par_columns": np.array(list(par_a.columns)), "a_ref_loglik": np.stack(ll_a),
+                "b_in_par": par_b.to_numpy(), "b_par_columns": np.array(list(par_b.columns)),
+                "b_in_data_info": np.stack([data_info[c] for c in names]), "b_ref_loglik": np.stack(ll_b)})
+    # standardised fit of the same partitions (logistic_model with data_info, intercept)
+    frames = [ref_shim.ref_logistic_model(df[df["partition_id"] == k], "label", fit_intercept=True, data_info=data_info)
+              for k in range(3)]
+    coef, smc, sig = frames_to_arrays(frames)
+    out.update({"b_ref_fit_columns": np.array(list(frames[0].columns)), "b_ref_fit_coef": coef,
+                "b_ref_fit_Sig_invMcoef": smc, "b_ref_fit_Sig_inv": sig})
+    # (c) dummy branch: numerics already in sorted order, one string-levelled categorical
+    rng = np.random.default_rng(22)
+    n = 5000
+    carr_levels = np.array(list("ABCDEFGH"))
+    carrier = carr_levels[rng.choice(8, size=n, p=np.array([0.35, 0.25, 0.15, 0.08, 0.06, 0.05, 0.04, 0.02]))]
+    anum, znum = rng.standard_normal(n) * 2 + 1, rng.standard_normal(n) * 0.5 - 3
+    eta = -0.3 - 0.4 * (anum - 1) / 2 + 0.5 * (znum + 3) / 0.5 * 0.3 + 0.3 * (carrier == "B")
+    yv = (rng.random(n) < 1 / (1 + np.exp(-eta))).astype(float)
+    dfc = pd.DataFrame({"partition_id": np.zeros(n), "y": yv, "anum": anum, "znum": znum, "Carrier": carrier})
+    dm = ref_shim.ref_dummies()
+    counts = dm.dummy_factors_counts(dfc, ["Carrier"])
+    import contextlib, io, tempfile
+    with tempfile.TemporaryDirectory() as td, contextlib.redirect_stdout(io.StringIO()):
+        info = dm.select_dummy_factors(counts, [0.8], "000_OTHERS", os.path.join(td, "d.pkl"))
+    base = ["Carrier_000_OTHERS"]
+    descc = dfc[["anum", "znum"]].describe()
+    dinfo = {c: descc[c].to_numpy() for c in ["anum", "znum"]}
+    frame = ref_shim.ref_logistic_model(dfc, "y", fit_intercept=True, dummy_info=info, dummy_factors_baseline=base,
+                                        data_info=dinfo)
+    par_c = pd.DataFrame(np.stack([frame["coef"].to_numpy(), rng.standard_normal(frame.shape[0]) * 0.3], axis=1),
+                         columns=["beta_byOLS", "beta_rand"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ll_c = m.logistic_model_eval(dfc.copy(), "y", par_c, fit_intercept=True, dummy_info=info,
+                                     dummy_factors_baseline=base, data_info=dinfo).to_numpy().ravel()
+    out.update({"c_in_y": yv, "c_in_anum": anum, "c_in_znum": znum, "c_in_Carrier": carrier, "c_in_keep_top": np.array([0.8]),
+                "c_in_baselines": np.array(base), "c_in_data_info": np.stack([dinfo[c] for c in ["anum", "znum"]]),
+                "c_ref_frame_columns": np.array(list(frame.columns)), "c_ref_frame": frame.to_numpy(dtype=float),
+                "c_in_par": par_c.to_numpy(), "c_par_columns": np.array(list(par_c.columns)), "c_ref_loglik": ll_c})
+    np.savez_compressed(os.path.join(GOLD, "eval_and_datainfo.npz"), **out)
+    print("eval golden: loglik a", ll_a[0], "b", ll_b[0], "c", ll_c, "frame c", frame.shape, list(frame.columns))
+
+
 def main():
     assert ref_shim.available(), "needs /root/reference"
     os.makedirs(GOLD, exist_ok=True)
@@ -217,6 +286,7 @@ def main():
     golden_sim("sim_p50_n40000_k4", 40_000, 50, 4, 9)
     golden_lars()
     golden_dummies()
+    golden_eval()
 
 
 if __name__ == "__main__":

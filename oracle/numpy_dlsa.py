@@ -488,7 +488,7 @@ def logistic_model_frame(sample_df, Y_name, fit_intercept=False, dummy_info=[], 
                 X[:, j] = (df[c].astype(str) == name[len(c) + 1:]).to_numpy(dtype=np.float64)
         std_cols = numeric
     else:
-        X = sample_df[xcols].to_numpy(dtype=np.float64)
+        X = np.array(sample_df[xcols].to_numpy(dtype=np.float64))  # a writable copy (pandas 3 hands out read-only views)
         std_cols = xcols
     if data_info is not None and len(data_info) > 0:
         for name in std_cols:

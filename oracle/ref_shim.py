@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE ONLY — runs the *reference's own functions* under in-process compat shims.
 
-Usable only where ``/root/reference`` exists (the build container).  It is how the oracle
-(``oracle/numpy_dlsa.py``) is pinned and how ``tests/golden/*.npz`` are minted
-(``oracle/make_golden.py``).  Nothing in the product path, the ``-m gpu`` tests, ``smoke()`` or
-``bench.py`` imports this module; the GPU box has no ``/root/reference``.
+Usable where the reference tree exists: ``/root/reference`` in the build container, or the git-ignored
+``baseline/_ref`` install of the unmodified reference that travels to the GPU box.  It is how the oracle
+(``oracle/numpy_dlsa.py``) is pinned, how ``tests/golden/*.npz`` are minted (``oracle/make_golden.py``) and what
+``bench.py --impl reference`` / the ``cpu_baseline`` leg time (``oracle/ref_cpu.py``).  Nothing in the product path,
+the ``-m gpu`` tests or ``smoke()`` imports this module.
 
 The shims do not change the reference's arithmetic:
   1. ``np.float`` / ``np.NAN`` aliases so ``dlsa/lsa.py:12,23,90`` import under numpy 2.
@@ -15,6 +16,8 @@ The shims do not change the reference's arithmetic:
   5. ``lars_lsa`` is called with ``np.matrix`` inputs (``dlsa/lsa.py:108,114`` need matrix ``*``).
   6. ``dlsa_mapred``'s Spark calls are emulated with a pandas group-sum; lines
      ``dlsa/dlsa.py:44-59`` are then followed literally.
+  7. ``pd.DataFrame({name: scalar})`` (``dlsa/models.py:224``: ``np.sum(DataFrame)`` is a scalar under pandas >= 2,
+     a one-element Series under the pinned pandas) -> one-row frame.
 """
 from __future__ import annotations
 
@@ -27,7 +30,22 @@ import warnings
 import numpy as np
 import pandas as pd
 
-REFERENCE_ROOT = os.environ.get("DLSA_REFERENCE_ROOT", "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference_root() -> str:
+    """The reference tree: $DLSA_REFERENCE_ROOT, else /root/reference (the build container), else the git-ignored
+    install under baseline/_ref (``pip install --target baseline/_ref`` of the unmodified reference, made by
+    ``__graft_entry__.build()``; it travels to the GPU box with the snapshot so that ``bench.py --impl reference`` can
+    time the reference's own functions there)."""
+    cands = [os.environ.get("DLSA_REFERENCE_ROOT"), "/root/reference", os.path.join(_ROOT, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "dlsa", "models.py")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def available() -> bool:
@@ -54,6 +72,14 @@ class _PandasCompat(types.ModuleType):
     @staticmethod
     def concat(objs, axis=0, **kw):  # dlsa/models.py:142 passes axis positionally
         return pd.concat(objs, axis=axis, **kw)
+
+    @staticmethod
+    def DataFrame(data=None, *a, **kw):
+        # dlsa/models.py:222-224 builds a frame from {name: np.sum(one-column DataFrame)}: a one-element Series per name
+        # under the pinned pandas, a scalar under pandas >= 2 (np.sum(df) reduces over both axes) -> one-row frame
+        if isinstance(data, dict) and data and all(np.isscalar(v) for v in data.values()) and not a and "index" not in kw:
+            return pd.DataFrame(data, index=[0], **kw)
+        return pd.DataFrame(data, *a, **kw)
 
     @staticmethod
     def get_dummies(**kw):  # dlsa/models.py:62-65 asks for sparse=True

@@ -100,10 +100,11 @@ def test_sdummies_level_rule():
 
 def test_synth_host_restatement_is_deterministic():
     from dlsa_b200 import synth
-    u = synth.host_uniform(7, np.arange(5, dtype=np.uint64)[:, None], np.arange(3, dtype=np.uint64)[None, :])
+    from oracle import synth_host
+    u = synth_host.host_uniform(7, np.arange(5, dtype=np.uint64)[:, None], np.arange(3, dtype=np.uint64)[None, :])
     assert u.shape == (5, 3) and np.all((u >= 0) & (u < 1))
-    assert np.array_equal(u, synth.host_uniform(7, np.arange(5, dtype=np.uint64)[:, None], np.arange(3, dtype=np.uint64)[None, :]))
-    big = synth.host_uniform(1, np.arange(200000, dtype=np.uint64), np.uint64(0))
+    assert np.array_equal(u, synth_host.host_uniform(7, np.arange(5, dtype=np.uint64)[:, None], np.arange(3, dtype=np.uint64)[None, :]))
+    big = synth_host.host_uniform(1, np.arange(200000, dtype=np.uint64), np.uint64(0))
     assert abs(big.mean() - 0.5) < 5e-3 and abs(big.var() - 1 / 12) < 2e-3
     off = synth.equal_partition_offsets(100_000_000, 1024)
     sizes = (off[1:] - off[:-1])
@@ -112,7 +113,7 @@ def test_synth_host_restatement_is_deterministic():
 
 
 def test_bench_contract_reference_arm_and_no_gpu_failure():
-    """bench.py --impl reference runs the reference's CPU path (oracle/ref_port.py) and prints ONE JSON line with the
+    """bench.py --impl reference runs the reference's CPU path (oracle/ref_cpu.py) and prints ONE JSON line with the
     contract's keys; without a GPU the product arm must fail loudly instead of falling back to anything."""
     import json
     import sys
@@ -127,7 +128,10 @@ def test_bench_contract_reference_arm_and_no_gpu_failure():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["metric"] == "dlsa_rows_per_sec" and d["unit"] == "rows/s" and d["value"] > 0
-    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "port"
+    from oracle import ref_shim
+    assert d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_shim.available() else "port")
+    assert d["config"]["workload"].startswith("c2: simulated logistic") and "sample" in d["config"]
     if not torch.cuda.is_available():
         out = subprocess.run([sys.executable, bench, "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
                              timeout=300)

@@ -112,6 +112,29 @@ def test_cat_pass_equals_dense_cuda_pass_on_expanded_matrix(eng):
     assert torch.equal(H2[0], H1[0])
 
 
+def test_airline_generator_is_counter_based_and_matches_host(eng):
+    """The compact airline-shaped stream (BASELINE configs[2] input) is keyed by (seed, global row): any sharding sees
+    the same rows, and the NumPy restatement in oracle/synth_host.py reproduces it."""
+    from dlsa_b200 import synth
+    from oracle import synth_host
+    n, seed, row0 = 20_000, 5, 987_654_321
+    num, codes, n_levels, y = synth.airline_shaped_device(n, seed, "cuda", row0=row0)
+    assert n_levels == [11, 6, 7, 75, 75]
+    b0, bnum, blev = synth.airline_truth()
+    hn, hc, eta, u = synth_host.airline_shaped_host(n, seed, synth.AIRLINE_LEVELS, synth.airline_cdfs(), b0, bnum, blev,
+                                                    row0=row0)
+    assert np.array_equal(codes.cpu().numpy(), hc)                      # integer work: bit-exact
+    assert np.max(np.abs(num.cpu().numpy() - hn)) < 1e-12               # Box-Muller: log / cospi differ by ulps
+    yh = (u < 1 / (1 + np.exp(-eta))).astype(np.float64)
+    assert np.mean(y.cpu().numpy() != yh) < 1e-3                        # identical up to rounding at the threshold
+    share0 = float((codes[:, 3] == -1).double().mean())                # Zipf(1) over 76 levels: baseline share 1/H_76
+    assert abs(share0 - 1.0 / np.sum(1.0 / np.arange(1, 77))) < 0.02
+    a = synth.airline_shaped_device(7_000, seed, "cuda", row0=row0)
+    b = synth.airline_shaped_device(13_000, seed, "cuda", row0=row0 + 7_000)
+    assert torch.equal(torch.cat([a[0], b[0]]), num) and torch.equal(torch.cat([a[1], b[1]]), codes)
+    assert torch.equal(torch.cat([a[3], b[3]]), y)
+
+
 def test_cat_fit_matches_oracle_fit_and_selection(eng):
     """Whole map -> combine -> LARS on the compact airline-shaped design vs the oracle run on the expanded matrix."""
     from dlsa_b200 import synth

@@ -227,3 +227,44 @@ def test_poisson_model_frame():
     assert list(out.columns) == ["par_id", "coef", "Sig_invMcoef", "intercept"] + [f"x{i}" for i in range(p)]
     assert np.max(np.abs(out["coef"].to_numpy() - c0)) < 1e-9
     assert np.linalg.norm(out.iloc[:, 3:].to_numpy() - S0) / np.linalg.norm(S0) < 1e-9
+
+
+def test_model_eval_and_data_info_against_reference_goldens():
+    """f-1: logistic_model_eval / logistic_model_eval_sdf (dlsa/models.py:151-225, dlsa/model_eval.py:10-42) and the
+    standardised fit logistic_model(..., data_info) (:99-101) against outputs of the REFERENCE's own functions
+    (tests/golden/eval_and_datainfo.npz, minted by oracle/make_golden.py::golden_eval)."""
+    from dlsa.models import logistic_model, logistic_model_eval
+    from dlsa.model_eval import logistic_model_eval_sdf
+    from dlsa import dummies
+    from test_oracle_pinned import _eval_golden_frames
+    g, df, names, dfc = _eval_golden_frames()
+    K = int(g["a_in_K"])
+    par_a = pd.DataFrame(g["a_in_par"], columns=[str(c) for c in g["a_par_columns"]])
+    par_b = pd.DataFrame(g["b_in_par"], columns=[str(c) for c in g["b_par_columns"]])
+    dinfo = {c: g["b_in_data_info"][j] for j, c in enumerate(names)}
+    for k in range(K):
+        part = df[df["partition_id"] == k]
+        la = logistic_model_eval(part, "label", par_a)
+        assert list(la.columns) == list(par_a.columns)
+        assert np.allclose(la.to_numpy()[0], g["a_ref_loglik"][k], rtol=1e-11)
+        lb = logistic_model_eval(part, "label", par_b, fit_intercept=True, data_info=dinfo)
+        assert np.allclose(lb.to_numpy()[0], g["b_ref_loglik"][k], rtol=1e-11)
+        fr = logistic_model(part, "label", fit_intercept=True, data_info=dinfo)
+        assert list(fr.columns) == [str(c) for c in g["b_ref_fit_columns"]]
+        assert np.max(np.abs(fr["coef"].to_numpy() - g["b_ref_fit_coef"][k])) < 1e-8
+        assert relfro(fr.iloc[:, 3:].to_numpy(), g["b_ref_fit_Sig_inv"][k]) < 1e-9
+        assert np.max(np.abs(fr["Sig_invMcoef"].to_numpy() - g["b_ref_fit_Sig_invMcoef"][k])) < 1e-6
+    tot = logistic_model_eval_sdf(df, par_a, False, "label", [], [], [])     # the global value = sum over partitions
+    assert np.allclose(tot.to_numpy()[0], g["a_ref_loglik"].sum(0), rtol=1e-11)
+    # dummy branch + intercept + standardisation, both device routes behind the facade
+    info = dummies.select_dummy_factors(dummies.dummy_factors_counts(dfc, ["Carrier"]), [float(g["c_in_keep_top"][0])])
+    base = [str(b) for b in g["c_in_baselines"]]
+    dinfo_c = {c: g["c_in_data_info"][j] for j, c in enumerate(["anum", "znum"])}
+    fr = logistic_model(dfc, "y", fit_intercept=True, dummy_info=info, dummy_factors_baseline=base, data_info=dinfo_c)
+    assert list(fr.columns) == [str(c) for c in g["c_ref_frame_columns"]]
+    assert np.max(np.abs(fr["coef"].to_numpy() - g["c_ref_frame"][:, 1])) < 1e-8
+    assert relfro(fr.iloc[:, 3:].to_numpy(), g["c_ref_frame"][:, 3:]) < 1e-9
+    par_c = pd.DataFrame(g["c_in_par"], columns=[str(c) for c in g["c_par_columns"]])
+    lc = logistic_model_eval(dfc, "y", par_c, fit_intercept=True, dummy_info=info, dummy_factors_baseline=base,
+                             data_info=dinfo_c)
+    assert np.allclose(lc.to_numpy()[0], g["c_ref_loglik"], rtol=1e-10)

@@ -224,3 +224,45 @@ def test_poisson_oracle_against_sklearn_glm():
         sk = PoissonRegressor(alpha=0.0, fit_intercept=icpt, tol=1e-12, max_iter=2000, solver="newton-cholesky").fit(X, y)
         ref = np.r_[sk.intercept_, sk.coef_] if icpt else sk.coef_
         assert np.max(np.abs(coef - ref)) < 1e-7
+
+
+def _eval_golden_frames():
+    """Inputs of tests/golden/eval_and_datainfo.npz rebuilt from their recipe (oracle/make_golden.py::golden_eval)."""
+    import pandas as pd
+    g = load_golden("eval_and_datainfo.npz")
+    pid, y, X, _ = onp.simulate_logistic(int(g["a_in_n"]), int(g["a_in_p"]), "systematic", int(g["a_in_K"]),
+                                         seed=int(g["a_in_seed"]))
+    names = ["x" + str(i) for i in range(X.shape[1])]
+    df = pd.DataFrame(np.concatenate([pid[:, None], y[:, None], X], axis=1), columns=["partition_id", "label"] + names)
+    dfc = pd.DataFrame({"partition_id": np.zeros(len(g["c_in_y"])), "y": g["c_in_y"], "anum": g["c_in_anum"],
+                        "znum": g["c_in_znum"], "Carrier": g["c_in_Carrier"]})
+    return g, df, names, dfc
+
+
+def test_oracle_loglik_and_standardised_fit_against_reference_goldens():
+    """logistic_model_eval (dlsa/models.py:151-225) and logistic_model(..., data_info) (:99-101) as run by the
+    reference: the oracle's log-likelihood and its standardised fit reproduce the frozen outputs."""
+    g, df, names, dfc = _eval_golden_frames()
+    K = int(g["a_in_K"])
+    dinfo = {c: g["b_in_data_info"][j] for j, c in enumerate(names)}
+    for k in range(K):
+        part = df[df["partition_id"] == k]
+        Xk, yk = part[names].to_numpy(), part["label"].to_numpy()
+        assert np.allclose(onp.logistic_loglik(Xk, yk, g["a_in_par"]), g["a_ref_loglik"][k], rtol=1e-12)
+        Xs = (Xk - g["b_in_data_info"][:, 1]) / g["b_in_data_info"][:, 2]
+        Xs1 = np.concatenate([np.ones((Xs.shape[0], 1)), Xs], axis=1)
+        assert np.allclose(onp.logistic_loglik(Xs1, yk, g["b_in_par"]), g["b_ref_loglik"][k], rtol=1e-12)
+        fr = onp.logistic_model_frame(part, "label", fit_intercept=True, data_info=dinfo)
+        assert list(fr.columns) == [str(c) for c in g["b_ref_fit_columns"]]
+        assert np.max(np.abs(fr["coef"].to_numpy() - g["b_ref_fit_coef"][k])) < 1e-8
+        assert relfro(fr.iloc[:, 3:].to_numpy(), g["b_ref_fit_Sig_inv"][k]) < 1e-9
+    # dummy branch + intercept + standardisation (case c)
+    info = onp.select_dummy_factors({"Carrier": dict(zip(*np.unique(dfc["Carrier"], return_counts=True)))}, [0.8])
+    counts = dfc["Carrier"].value_counts()
+    info = onp.select_dummy_factors({"Carrier": {k: int(v) for k, v in counts.items()}}, [float(g["c_in_keep_top"][0])])
+    dinfo_c = {c: g["c_in_data_info"][j] for j, c in enumerate(["anum", "znum"])}
+    fr = onp.logistic_model_frame(dfc, "y", fit_intercept=True, dummy_info=info,
+                                  dummy_factors_baseline=[str(b) for b in g["c_in_baselines"]], data_info=dinfo_c)
+    assert list(fr.columns) == [str(c) for c in g["c_ref_frame_columns"]]
+    assert np.max(np.abs(fr.to_numpy(dtype=float)[:, 1] - g["c_ref_frame"][:, 1])) < 1e-8
+    assert relfro(fr.to_numpy(dtype=float)[:, 3:], g["c_ref_frame"][:, 3:]) < 1e-9
