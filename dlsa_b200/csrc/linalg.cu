@@ -10,7 +10,8 @@
 
 namespace dlsa {
 
-constexpr int kCholThreads = 256;
+constexpr int kCholThreads = 256;          // p <= 160: factor in shared memory
+constexpr int kCholThreadsBlocked = 512;   // p > 160: 16 warps hide the global-memory latency of the trailing update
 constexpr int kCholSmemMaxP = 160;  // p*p*8 <= 204,800 B fits one CTA's shared memory
 
 // In-place Cholesky A = L L' on the lower triangle of L[p][ld] (right-looking, one CTA), then
@@ -247,14 +248,14 @@ __device__ void chol_blocked_solve_cta(const double* L, int ld, int p, double* x
 
 // mode 0: Newton update (beta += delta with damping / convergence bookkeeping); mode 1: plain solve
 template <bool SMEM>
-__global__ void __launch_bounds__(kCholThreads) chol_kernel(const double* __restrict__ A, const double* __restrict__ b,
+__global__ void __launch_bounds__(SMEM ? kCholThreads : kCholThreadsBlocked) chol_kernel(const double* __restrict__ A, const double* __restrict__ b,
                                                             int K, int p, int mode, double* beta, double* x_out,
                                                             double* max_delta, int* status, int* active, int* iters,
                                                             int* n_active, double tol, double damp_above,
                                                             double damp_factor, double* gws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int ok_s;
-    __shared__ double md_s[kCholThreads / 32];
+    __shared__ double md_s[kCholThreadsBlocked / 32];
     const int k = blockIdx.x;
     if (mode == 0 && active != nullptr && active[k] == 0) return;
     double* xs = reinterpret_cast<double*>(smem_raw);  // [p]
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(kCholThreads) chol_kernel(const double* __rest
     if ((threadIdx.x & 31) == 0) md_s[threadIdx.x >> 5] = md;
     __syncthreads();
     md = md_s[0];
-    for (int w = 1; w < kCholThreads / 32; w++) md = fmax(md, md_s[w]);
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) md = fmax(md, md_s[w]);
     if (!ok || !isfinite(md)) {
         if (threadIdx.x == 0) {
             status[k] = DLSA_ST_NOT_SPD;
@@ -349,7 +350,7 @@ int chol_launch(const double* A, const double* b, int K, int p, int mode, double
         const int mmax = (p > kNB) ? ((p - kNB + 7) & ~7) : 8;
         const size_t smem = ((size_t)((p + 1) & ~1) + (size_t)kNB * kDPitch + kNB + (size_t)mmax * kPPitch) * sizeof(double);
         DLSA_CUDA(cudaFuncSetAttribute(chol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        chol_kernel<false><<<K, kCholThreads, smem, st>>>(A, b, K, p, mode, beta, x_out, max_delta, status, active,
+        chol_kernel<false><<<K, kCholThreadsBlocked, smem, st>>>(A, b, K, p, mode, beta, x_out, max_delta, status, active,
                                                           iters, n_active, tol, damp_above, damp_factor,
                                                           static_cast<double*>(workspace));
     }

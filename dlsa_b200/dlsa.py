@@ -10,28 +10,29 @@ from .lsa import _device, _to_dev
 
 
 def _fits_from_frame(pdf: pd.DataFrame):
-    """Stacked per-partition frames (K*p rows x (3+p)) -> PartitionFits tensors.  All-zero rows (the zero frame of
-    a skipped chunk, dlsa/models.py:84-91) carry no information and are dropped; the remaining rows are grouped
-    by ``par_id`` exactly as ``groupby('par_id')`` does (dlsa/dlsa.py:30)."""
+    """Stacked per-partition frames (K*p rows x (3+p)) -> PartitionFits tensors.  The zero frame of a skipped chunk
+    (dlsa/models.py:84-91: p all-zero rows) carries no information and is dropped as a BLOCK of p consecutive rows; the
+    rows that remain are grouped by ``par_id`` exactly as ``groupby('par_id')`` does (dlsa/dlsa.py:30).  A rank whose
+    local frames are all zero returns K = 0 tensors: its packed buffer is zero and the "empty" error of
+    dlsa/dlsa.py:36-39 is raised after the allreduce, on every rank at once (engine.combine_partitions)."""
     cols = list(pdf.columns)
     p = len(cols) - 3
     vals = pdf.to_numpy(dtype=np.float64)
-    keep = np.any(vals[:, 1:] != 0.0, axis=1)
-    vals = vals[keep]
-    if vals.shape[0] == 0:
-        raise Exception("Zero-length grouped pandas DataFrame obtained, check the input.")  # dlsa/dlsa.py:36-39
-    order = np.argsort(vals[:, 0], kind="stable")
-    vals = vals[order]
-    counts = np.bincount(vals[:, 0].astype(np.int64), minlength=p)
-    if len(counts) != p or np.any(counts != counts[0]):
+    if vals.shape[0] % p != 0:
+        raise ValueError("dlsa_mapred: the mapped frame must stack whole p-row partition frames")
+    blocks = vals.reshape(-1, p, 3 + p)
+    blocks = blocks[np.any(blocks[:, :, 1:] != 0.0, axis=(1, 2))]
+    K = blocks.shape[0]
+    if K and not np.array_equal(np.sort(blocks[:, :, 0], axis=1), np.broadcast_to(np.arange(p), (K, p))):
         raise ValueError("dlsa_mapred: every par_id must appear once per fitted partition")
-    K = int(counts[0])
-    blk = vals.reshape(p, K, 3 + p).transpose(1, 0, 2)  # [K, p, 3+p]
+    if K:
+        order = np.argsort(blocks[:, :, 0], axis=1, kind="stable")
+        blocks = np.take_along_axis(blocks, order[:, :, None], axis=1)   # rows of each frame in par_id order
     dev = _device()
     return engine.PartitionFits(
-        coef=torch.as_tensor(np.ascontiguousarray(blk[:, :, 1]), device=dev),
-        Sig_inv=torch.as_tensor(np.ascontiguousarray(blk[:, :, 3:]), device=dev),
-        Sig_invMcoef=torch.as_tensor(np.ascontiguousarray(blk[:, :, 2]), device=dev),
+        coef=torch.as_tensor(np.ascontiguousarray(blocks[:, :, 1]), device=dev).reshape(K, p),
+        Sig_inv=torch.as_tensor(np.ascontiguousarray(blocks[:, :, 3:]), device=dev).reshape(K, p, p),
+        Sig_invMcoef=torch.as_tensor(np.ascontiguousarray(blocks[:, :, 2]), device=dev).reshape(K, p),
         status=torch.zeros(K, dtype=torch.int32, device=dev), iters=torch.zeros(K, dtype=torch.int32, device=dev),
         loglik=None, passes=0, n_rows=0), cols[3:]
 

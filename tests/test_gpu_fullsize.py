@@ -87,6 +87,7 @@ def test_warm_start_falls_back_to_cold_start_when_a_partition_fails(eng):
 
 def test_c2_full_size_properties(eng):
     """BASELINE.json configs[1]: n=1e8, p=50, 1024 partitions on one GPU (40.8 GB of float64)."""
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     if free < 60e9:
         pytest.skip("needs ~45 GB of free HBM")
@@ -175,3 +176,101 @@ def test_c5_shaped_p500_many_small_partitions(eng):
     assert np.max(np.abs(bp - rp["beta"])) < 1e-6
     assert path.argmin_BIC == int(np.argmin(rp["BIC"])) and path.argmin_AIC == int(np.argmin(rp["AIC"]))
     assert np.allclose(path.BIC.cpu().numpy(), rp["BIC"], rtol=1e-9)
+
+
+def test_c3_compact_full_size_against_oracle_on_sampled_partitions(eng):
+    """BASELINE.json configs[2] through the compact categorical pass K1c: the WHOLE airline-shaped data set (n = 1.2e8,
+    K = 120 partitions of 1e6 rows, p = 182) on one GPU.  The oracle cannot fit 1e6 x 182 in seconds, but ONE pass of it
+    on a sampled partition's expanded design at the returned coefficients pins both halves of the claim: its H is the
+    returned Sig_inv (<= 1e-9 rel. Frobenius) and its Newton step H^-1 g is below 1e-8, i.e. the returned coefficients
+    are that partition's MLE.  Plus shard invariance of the counter-based generator and the combine identity."""
+    from dlsa_b200 import synth
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs ~15 GB of free HBM")
+    dev = torch.device("cuda", 0)
+    n, K, seed = 120_000_000, 120, 20210517
+    num = torch.empty(n, synth.AIRLINE_NUM, dtype=torch.float64, device=dev)
+    codes = torch.empty(n, len(synth.AIRLINE_LEVELS), dtype=torch.int32, device=dev)
+    y = torch.empty(n, dtype=torch.float64, device=dev)
+    for s in range(0, n, 20_000_000):
+        _, _, n_levels, _ = synth.airline_shaped_device(20_000_000, seed, dev, row0=s,
+                                                        out=(num[s:s + 20_000_000], codes[s:s + 20_000_000], y[s:s + 20_000_000]))
+    off = synth.equal_partition_offsets(n, K, dev)
+    fits = eng.fit_logistic_partitions_cat(num, codes, n_levels, y, off, fit_intercept=True)
+    assert int(fits.status.abs().sum().item()) == 0
+    p = fits.coef.shape[1]
+    assert p == 182
+    comb = eng.combine_partitions(fits)
+    S = fits.Sig_inv.sum(0)
+    assert relfro_t(comb.Sig_inv_sum, S) < 1e-13
+    rhs = fits.Sig_invMcoef.sum(0)
+    assert (S @ comb.beta_byOLS - rhs).abs().max().item() < 1e-9 * rhs.abs().max().item()
+    b0, bnum, blev = synth.airline_truth()
+    truth = np.r_[b0, bnum, blev]
+    assert np.max(np.abs(comb.beta_byOLS.cpu().numpy() - truth)) < 0.02     # 1.2e8 rows recover the data law
+    offh = off.cpu().numpy()
+    for k in (0, 77):
+        lo, hi = int(offh[k]), int(offh[k + 1])
+        # the shard [lo, hi) regenerated on its own is the same data (what a rank of an 8-GPU run would hold)
+        a = synth.airline_shaped_device(hi - lo, seed, dev, row0=lo)
+        assert torch.equal(a[0], num[lo:hi]) and torch.equal(a[1], codes[lo:hi]) and torch.equal(a[3], y[lo:hi])
+        Xk = onp.expand_onehot(num[lo:hi].cpu().numpy(), codes[lo:hi].cpu().numpy(), n_levels)
+        X1 = np.concatenate([np.ones((Xk.shape[0], 1)), Xk], axis=1)
+        g0, H0, _ = onp.irls_pass(X1, y[lo:hi].cpu().numpy(), fits.coef[k].cpu().numpy())
+        assert np.linalg.norm(fits.Sig_inv[k].cpu().numpy() - H0) / np.linalg.norm(H0) < 1e-9
+        assert np.max(np.abs(np.linalg.solve(H0, g0))) < 1e-8
+        del Xk, X1
+
+
+def test_c5_full_size_k8192_properties(eng):
+    """BASELINE.json configs[4] at its full size: p = 500 sparse-truth logistic, K = 8192 partitions of 2500 rows
+    (81.9 GB of float64), 'lar' path + BIC.  Properties: every partition converged; the oracle's own fit of three sampled
+    partitions; the score equation on a block of partitions; the combine identity; the path has p + 1 knots with
+    decreasing RSS and its BIC choice contains the 25 true variables."""
+    from dlsa_b200 import synth
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 130e9:
+        pytest.skip("needs ~120 GB of free HBM")
+    dev = torch.device("cuda", 0)
+    K, nk, p = 8192, 2500, 500
+    n = K * nk
+    beta = np.r_[np.ones(25), np.zeros(p - 25)]
+    X = torch.empty(n, p, dtype=torch.float64, device=dev)
+    y = torch.empty(n, dtype=torch.float64, device=dev)
+    for s in range(0, n, 1_000_000):
+        m = min(1_000_000, n - s)
+        synth.simulate_logistic_device(m, p, 7, dev, row0=s, beta=beta, out=(X[s:s + m], y[s:s + m]))
+    off = synth.equal_partition_offsets(n, K, dev)
+    fits, comb, path = eng.dlsa_fit(X, y, off, sample_size=n, type="lar", max_part_rows=nk)
+    assert int(fits.status.abs().sum().item()) == 0 and comb.K_eff == K and not fits.cold_restart
+    for k in (0, 4097, 8191):
+        sl = slice(k * nk, (k + 1) * nk)
+        c0, S0, _ = onp.logistic_fit(X[sl].cpu().numpy(), y[sl].cpu().numpy())
+        assert np.max(np.abs(fits.coef[k].cpu().numpy() - c0)) < 1e-8
+        assert np.linalg.norm(fits.Sig_inv[k].cpu().numpy() - S0) / np.linalg.norm(S0) < 1e-9
+    # score equation on partitions 1000..1063: a fresh pass at the returned coefficients reproduces the returned Sig_inv
+    # (to rounding: 64 partitions are cut into row slices the 8192-partition launch does not use, so the summation order
+    # differs) and leaves a Newton step below the solver tolerance
+    k0, k1 = 1000, 1064
+    offb = (off[k0:k1 + 1] - off[k0]).contiguous()
+    g, H, _ = eng.irls_pass(X[k0 * nk:k1 * nk], y[k0 * nk:k1 * nk], offb, fits.coef[k0:k1].contiguous(), want_loglik=False)
+    assert relfro_t(H, fits.Sig_inv[k0:k1]) < 1e-13
+    assert torch.linalg.solve(H, g.unsqueeze(-1)).abs().max().item() < 1e-8
+    del X, y
+    torch.cuda.empty_cache()
+    # combine identity in chunks (16 GB of Sig_inv): fixed-order sum == the kernel's sum, theta solves the normal equation
+    S = torch.zeros(p, p, dtype=torch.float64, device=dev)
+    for c in range(0, K, 512):
+        S += fits.Sig_inv[c:c + 512].sum(0)
+    assert relfro_t(comb.Sig_inv_sum, S) < 1e-12
+    rhs = fits.Sig_invMcoef.sum(0)
+    assert (comb.Sig_inv_sum @ comb.beta_byOLS - rhs).abs().max().item() < 1e-9 * rhs.abs().max().item()
+    assert (comb.beta_byONESHOT - fits.coef.mean(0)).abs().max().item() < 1e-12
+    assert path.beta.shape == (p + 1, p) and int(path.dof[-1].item()) == p
+    rss = path.RSS.cpu().numpy()
+    assert np.all(np.diff(rss) <= 1e-9 * rss[0])
+    sel = (path.beta[path.argmin_BIC] != 0).cpu().numpy()
+    assert sel[:25].all() and sel.sum() <= 40
