@@ -7,9 +7,12 @@
 // A row of the expanded X is z = [1 | x_1..x_q] (q <= 7 numerics) plus ONE 1 per categorical column, so
 //   H[z, z]           = sum w z z'                         one DMMA per 4 rows (8x8 tile)
 //   H[level, z]       = sum_{rows at that level} w z'      scatter-add into a WARP-PRIVATE shared-memory table
-//   g[level]          = sum_{rows at that level} r          [level][9]: 8 lanes per (row, categorical) + 1 for g, rows
-//                                                          taken two at a time with in-register forwarding when both
-//                                                          hit the same level — no atomics, fixed summation order
+//   g[level]          = sum_{rows at that level} r          [level][9]: lane = (categorical, column); the row stage leaves
+//                                                          (w z', r) and the table offset of every (row, categorical) in
+//                                                          shared memory, so a row pair costs 4 loads + 2 adds + 2 stores
+//                                                          per lane, the second row's sum forwarded in registers when both
+//                                                          hit the same level — no atomics, fixed summation order; codes
+//                                                          of baseline levels point at a sink row (no predicates)
 //   H[level, level]   = H[level, 1]  (the intercept column of the block above)
 //   H[level, level']  = sum w over rows holding both       (different categorical columns) — a weighted 2-D histogram:
 //                                                          64-bit fixed-point RED.ADD into an L2-resident table
@@ -29,7 +32,7 @@ namespace {
 constexpr int kCatMaxC = 8;      // categorical columns
 constexpr int kCatMaxNum = 7;    // numeric columns (z = [1 | numerics] fills one 8-wide tile)
 constexpr int kCatMaxWarps = 12;
-constexpr int kCatStages = 3;
+constexpr int kCatStages = 2;
 constexpr int kCatMaxRowsPerCta = 1 << 20;
 constexpr int kCatMaxLevels = 248;  // one byte per level index, 0xFF = no level
 constexpr int kTabPitch = 9;        // doubles per level: w*z (8) | r
@@ -39,7 +42,9 @@ constexpr int kStageZ = 32 * kCatMaxNum * 8;
 constexpr int kStageC = 32 * kCatMaxC * 4;
 constexpr int kStageY = 32 * 8;
 constexpr int kStageBytes = kStageZ + kStageC + kStageY;  // 3072
-constexpr int kRowScratch = 32 * 16 + 32 * 8;              // (w, r) per row | packed level bytes per row
+constexpr int kWzPitch = 10;                               // doubles per row: w | w*z_1..7 | r | 0
+constexpr int kToPitch = 12;                                // ints per row: offsets of categoricals 0..7 | 4 x sink (idle lanes)
+constexpr int kRowScratch = 32 * kWzPitch * 8 + 32 * kToPitch * 4;  // (w z', r) per row | table byte offset per (row, categorical)
 
 struct CatArgs {
     const double* num;
@@ -91,14 +96,15 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_num = a.n_num, n_cat = a.n_cat;
-    const int tab_doubles = a.Lpad * kTabPitch;
+    const int tab_doubles = a.Lpad * kTabPitch;          // what the CTA reduction reads; the sink row follows it
+    const int tab_alloc = ((a.Lpad + 1) * kTabPitch + 1) & ~1;   // even: every warp's block stays 16-byte aligned
 
-    // shared: per warp [ring | row scratch | table] ; then beta (8 + Lpad)
-    const size_t per_warp = (size_t)kCatStages * kStageBytes + kRowScratch + (size_t)tab_doubles * 8;
+    // shared: per warp [ring | row scratch | table + sink row] ; then beta (8 + Lpad)
+    const size_t per_warp = (size_t)kCatStages * kStageBytes + kRowScratch + (size_t)tab_alloc * 8;
     unsigned char* mine = smem_raw + (size_t)warp * per_warp;
     unsigned char* ring = mine;
-    double* wr = reinterpret_cast<double*>(mine + kCatStages * kStageBytes);                       // [32][2]
-    unsigned long long* lv = reinterpret_cast<unsigned long long*>(mine + kCatStages * kStageBytes + 512);  // [32]
+    double* wz = reinterpret_cast<double*>(mine + kCatStages * kStageBytes);                              // [32][10]
+    int* toff = reinterpret_cast<int*>(mine + kCatStages * kStageBytes + 32 * kWzPitch * 8);              // [32][12]
     double* tab = reinterpret_cast<double*>(mine + kCatStages * kStageBytes + kRowScratch);
     double* bz = reinterpret_cast<double*>(smem_raw + (size_t)nwarps * per_warp);
     double* bl = bz + 8;
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
             else if (i - 8 < a.Ltot) v = bk[a.fit_intercept + n_num + (i - 8)];
             bz[i] = v;
         }
-        for (int i = lane; i < tab_doubles; i += 32) tab[i] = 0.0;
+        for (int i = lane; i < tab_alloc; i += 32) tab[i] = 0.0;
     }
     __syncthreads();
 
@@ -161,19 +167,22 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
         cp_async_commit();  // one (possibly empty) group per call keeps the wait_group arithmetic uniform
     };
 
-    // per-lane scatter slots: round q handles slot 32 q + lane = (categorical c, column j); j = 8 is the g column
-    int slot_sh[ROUNDS];    // bit shift of categorical c's byte in the packed level word, or -1 (idle lane)
-    int slot_j[ROUNDS];     // table column 0..8
-    int slot_z[ROUNDS];     // offset of the z value inside a numerics row, -1 => 1.0 (intercept / g), -2 => 0.0
+    // per-lane scatter slots: round q handles slot 32 q + lane = (categorical c, column j); j = 8 is the g column.  Idle
+    // lanes take "categorical 8", whose offset is always the sink row, and column 9 of the (w z', r) row, which is 0.0.
+    const uint32_t wz_u32 = smem_u32(wz), toff_u32 = smem_u32(toff), tab_u32 = smem_u32(tab);
+    const int sink_off = a.Lpad * kTabPitch * 8;
+    uint32_t slot_to[ROUNDS];   // shared address of toff[0][c]
+    uint32_t slot_wz[ROUNDS];   // shared address of wz[0][j]
+    uint32_t slot_tb[ROUNDS];   // shared address of tab[0][j]
 #pragma unroll
     for (int q = 0; q < ROUNDS; ++q) {
         const int sidx = 32 * q + lane;
-        int c = -1, j = 0;
+        int c = 8, j = 9;       // idle
         if (sidx < 8 * n_cat) { c = sidx >> 3; j = sidx & 7; }
         else if (sidx < 9 * n_cat) { c = sidx - 8 * n_cat; j = 8; }
-        slot_sh[q] = c < 0 ? -1 : 8 * c;
-        slot_j[q] = j;
-        slot_z[q] = (j == 0 || j == 8) ? -1 : (j - 1 < n_num ? j - 1 : -2);
+        slot_to[q] = toff_u32 + 4 * c;
+        slot_wz[q] = wz_u32 + 8 * j;
+        slot_tb[q] = tab_u32 + 8 * (j == 9 ? 0 : j);
     }
 
     double dz0 = 0.0, dz1 = 0.0, ll = 0.0;
@@ -213,7 +222,9 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
             }
         }
         int lev[NC];
-        unsigned long long packed = ~0ull;
+        int to[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) to[c] = sink_off;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             lev[c] = -1;
@@ -222,9 +233,9 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
                 if (code >= 0) {
                     lev[c] = a.cat_lo[c] + code;
                     eta += bl[lev[c]];
+                    to[c] = lev[c] * (kTabPitch * 8);
                 }
             }
-            packed = (packed & ~(0xFFull << (8 * c))) | ((unsigned long long)(lev[c] & 0xFF) << (8 * c));
         }
         double w = 0.0, r = 0.0;
         if (valid) {
@@ -237,64 +248,83 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
         gz[0] += r;
 #pragma unroll
         for (int j = 0; j < kCatMaxNum; ++j) gz[1 + j] = fma(r, z[j], gz[1 + j]);
-        *reinterpret_cast<double2*>(wr + 2 * lane) = make_double2(w, r);
-        lv[lane] = packed;
-        {
+        {   // (w, w z_1..7, r, 0) and the table offsets of this row
+            double2* wrow = reinterpret_cast<double2*>(wz + lane * kWzPitch);
+            wrow[0] = make_double2(w, w * z[0]);
+            wrow[1] = make_double2(w * z[1], w * z[2]);
+            wrow[2] = make_double2(w * z[3], w * z[4]);
+            wrow[3] = make_double2(w * z[5], w * z[6]);
+            wrow[4] = make_double2(r, 0.0);
+            int4* trow = reinterpret_cast<int4*>(toff + lane * kToPitch);
+            trow[0] = make_int4(to[0], to[1], to[2], to[3]);
+            trow[1] = make_int4(to[4], to[5], to[6], to[7]);
+            trow[2] = make_int4(sink_off, sink_off, sink_off, sink_off);
+        }
+        {   // weighted pair histogram: straight-line code, a pair with a baseline level (or an invalid row) adds into
+            // this lane's sink cell behind the table instead of branching around the RED
             const long long wfix = __double2ll_rn(w * kWScale);
+            int li[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) li[c] = lev[c] - a.cat_lo[c < n_cat ? c : 0];
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                if (lev[c] >= 0) {
 #pragma unroll
-                    for (int d = c + 1; d < NC; ++d)
-                        if (lev[d] >= 0)
-                            red_add_u64(pairs + a.pair_off[c * kCatMaxC + d] +
-                                            (lev[c] - a.cat_lo[c]) * (a.cat_lo[d + 1] - a.cat_lo[d]) +
-                                            (lev[d] - a.cat_lo[d]),
-                                        wfix);
+                for (int d = c + 1; d < NC; ++d) {
+                    if (d < n_cat) {  // warp-uniform
+                        const int idx = a.pair_off[c * kCatMaxC + d] + li[c] * (a.cat_lo[d + 1] - a.cat_lo[d]) + li[d];
+                        red_add_u64(pairs + ((lev[c] >= 0 && lev[d] >= 0) ? idx : a.npairs + lane), wfix);
+                    }
                 }
             }
         }
         __syncwarp();
 
-        // ---- dense z block: 8 k-steps of 4 rows, one DMMA each ------------------------------------------------------
+        // ---- dense z block: 8 k-steps of 4 rows, one DMMA each: A = z, B = w z (already in shared memory) ----------
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
             const int src = 4 * ks + (lane & 3);
             double zz = 1.0;
             if (jcol > 0) zz = (jcol - 1 < n_num) ? zs[src * n_num + jcol - 1] : 0.0;
-            dmma884(dz0, dz1, zz, wr[2 * src] * zz);
+            dmma884(dz0, dz1, zz, wz[src * kWzPitch + jcol]);
         }
 
         // ---- level blocks: scatter-add into the warp's table, two rows per step ------------------------------------
         // Lane (c, j) always owns column j of categorical c's levels, so successive rows that hit the same level are
         // ordered by program order of ONE thread; inside a row pair the second row's sum is forwarded in registers.
-#pragma unroll 4
-        for (int rp = 0; rp < 16; ++rp) {
-            const int ra = 2 * rp, rb = ra + 1;
-            const unsigned long long pa = lv[ra], pb = lv[rb];
+        // All loads of a pair (both rounds: their slots are disjoint) are issued before its stores.
+        uint32_t pa[ROUNDS], pb[ROUNDS];
+        double va[ROUNDS], vb[ROUNDS];
+        auto load_pair = [&](int rp) {   // table addresses and addends of rows 2 rp, 2 rp + 1 for this lane's slots
+            const uint32_t ra_t = (uint32_t)(2 * rp) * (kToPitch * 4u), ra_w = (uint32_t)(2 * rp) * (kWzPitch * 8u);
 #pragma unroll
             for (int q = 0; q < ROUNDS; ++q) {
-                if (slot_sh[q] >= 0) {
-                    const uint32_t la = (uint32_t)(pa >> slot_sh[q]) & 0xFFu;
-                    const uint32_t lb = (uint32_t)(pb >> slot_sh[q]) & 0xFFu;
-                    const int sel = slot_j[q] == 8 ? 1 : 0;
-                    double va = wr[2 * ra + sel], vb = wr[2 * rb + sel];
-                    if (slot_z[q] >= 0) {
-                        va *= zs[ra * n_num + slot_z[q]];
-                        vb *= zs[rb * n_num + slot_z[q]];
-                    } else if (slot_z[q] == -2) {
-                        va = 0.0;
-                        vb = 0.0;
-                    }
-                    const bool oka = la != 0xFFu, okb = lb != 0xFFu;
-                    double* qa = tab + (oka ? la : 0u) * kTabPitch + slot_j[q];
-                    double* qb = tab + (okb ? lb : 0u) * kTabPitch + slot_j[q];
-                    const double ta = *qa, tb = *qb;
-                    const double na = ta + va;
-                    const double nb = ((oka && la == lb) ? na : tb) + vb;
-                    if (oka) *qa = na;
-                    if (okb) *qb = nb;
-                }
+                int oa, ob;
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(oa) : "r"(slot_to[q] + ra_t));
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(ob) : "r"(slot_to[q] + ra_t + kToPitch * 4u));
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(va[q]) : "r"(slot_wz[q] + ra_w));
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(vb[q]) : "r"(slot_wz[q] + ra_w + kWzPitch * 8u));
+                pa[q] = slot_tb[q] + (uint32_t)oa;
+                pb[q] = slot_tb[q] + (uint32_t)ob;
+            }
+        };
+        load_pair(0);
+#pragma unroll 2
+        for (int rp = 0; rp < 16; ++rp) {
+            uint32_t ca[ROUNDS], cb[ROUNDS];
+            double ta[ROUNDS], tb[ROUNDS], xa[ROUNDS], xb[ROUNDS];
+#pragma unroll
+            for (int q = 0; q < ROUNDS; ++q) {
+                ca[q] = pa[q]; cb[q] = pb[q]; xa[q] = va[q]; xb[q] = vb[q];
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ta[q]) : "r"(ca[q]) : "memory");
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(tb[q]) : "r"(cb[q]) : "memory");
+            }
+            if (rp + 1 < 16) load_pair(rp + 1);   // the row scratch is not written inside this loop: safe to read ahead
+#pragma unroll
+            for (int q = 0; q < ROUNDS; ++q) {
+                const double na = ta[q] + xa[q];
+                const double nb = ((ca[q] == cb[q]) ? na : tb[q]) + xb[q];
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(ca[q]), "d"(na) : "memory");
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(cb[q]), "d"(nb) : "memory");
             }
         }
         __syncwarp();  // the stage and the row scratch are re-filled by the next iteration
@@ -431,19 +461,31 @@ void cat_plan(int K, int n_cat, const int* n_levels, int64_t max_part_rows, CatP
     }
     pl.Lpad = (pl.Ltot + 7) / 8 * 8;
     const int sms = cat_sm_count();
-    int64_t S = K < sms ? sms / K : 1;
-    const int64_t s_rows = (max_part_rows + 4095) / 4096;  // at least 4096 rows per CTA
-    if (S > s_rows) S = s_rows;
+    // slices per partition: one CTA per SM at a time, so K * S should fill whole waves of `sms` CTAs (K = 120, S = 1 leaves
+    // 19 % of the SMs idle; S = 6 gives 4.86 waves = 97 %).  The smallest S wins unless a larger one fills the waves 6 % better;
+    // every slice keeps at least 4096 rows and S <= 16 bounds the partial buffers.
+    const int64_t s_rows = (max_part_rows + 4095) / 4096;
+    int64_t s_cap = K <= 16 ? (2 * sms + K - 1) / K : 16;
+    if (s_cap > s_rows) s_cap = s_rows;
+    if (s_cap < 1) s_cap = 1;
+    double best = -1.0;
+    int64_t S = 1;
+    for (int64_t cand = 1; cand <= s_cap; ++cand) {
+        const int64_t u = (int64_t)K * cand;
+        const double eff = (double)u / (double)(((u + sms - 1) / sms) * sms);
+        if (eff > best + 0.06) { best = eff; S = cand; }
+    }
     const int64_t s_min = (max_part_rows + kCatMaxRowsPerCta - 1) / kCatMaxRowsPerCta;  // fixed-point headroom
     if (S < s_min) S = s_min;
     if (S < 1) S = 1;
     pl.S = (int)S;
     pl.stride_d = 80 + (int64_t)pl.Lpad * kTabPitch;
-    pl.stride_i = pl.npairs > 0 ? pl.npairs : 1;
+    pl.stride_i = pl.npairs + 32;  // + one sink cell per lane for pairs that involve a baseline level
     pl.bytes_d = (size_t)K * S * pl.stride_d * 8;
     pl.bytes_i = (size_t)K * S * pl.stride_i * 8;
     // as many warps as shared memory allows (each owns a ring, a row scratch and a level table)
-    const size_t per_warp = (size_t)kCatStages * kStageBytes + kRowScratch + (size_t)pl.Lpad * kTabPitch * 8;
+    const size_t per_warp = (size_t)kCatStages * kStageBytes + kRowScratch +
+                            (size_t)((((pl.Lpad + 1) * kTabPitch + 1) & ~1)) * 8;
     const size_t fixed = (size_t)(8 + pl.Lpad) * 8;
     const size_t budget = 227 * 1024;
     int warps = (int)((budget - fixed) / per_warp);
