@@ -388,6 +388,24 @@ def test_linear_large_p_tail_chunk_in_a_reused_stage(eng, sizes):
         assert abs(yh[k] - yk @ yk) < 1e-9 * (yk @ yk)
 
 
+def test_linear_p300_sixteen_row_chunks_with_ragged_tails(eng):
+    """Linear family at a width that takes 16-row chunks (two lanes per row in the link warps): partitions whose length
+    is not a multiple of 16, more chunks per slice than ring stages."""
+    rng = np.random.default_rng(33)
+    p, sizes = 300, [2500, 2503, 16 * 40 + 5, 1, 17]
+    n = int(np.sum(sizes))
+    X = rng.standard_normal((n, p))
+    y = X[:, :10] @ np.arange(1.0, 11.0) + rng.standard_normal(n)
+    off = ragged_offsets(sizes)
+    g, H, yty = eng.irls_pass(dev(X), dev(y), dev(off, torch.int64), None, False, 1, want_loglik=True)
+    Hh, gh, yh = H.cpu().numpy(), g.cpu().numpy(), yty.cpu().numpy()
+    for k in range(len(sizes)):
+        Xk, yk = X[off[k]:off[k + 1]], y[off[k]:off[k + 1]]
+        assert relfro(Hh[k], Xk.T @ Xk) < 1e-12
+        assert np.max(np.abs(gh[k] - Xk.T @ yk)) < 1e-9 * max(1.0, np.max(np.abs(Xk.T @ yk)))
+        assert abs(yh[k] - yk @ yk) <= 1e-9 * (yk @ yk)
+
+
 def test_glm_pass_on_a_window_of_the_offsets(eng):
     """A window part_offsets[lo:hi+1] of a longer offsets array with the SHARED X (what parallel.shard_partitions hands
     out): the streaming link kernel's w / r buffers are indexed relative to the window's first row."""
