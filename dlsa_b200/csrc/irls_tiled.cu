@@ -91,7 +91,7 @@ __device__ __forceinline__ void t_mbar_arrive(uint32_t bar) {
 template <bool LOGIT, int NF, int PAT, int NH, bool HASG>
 __device__ __forceinline__ void tiled_chunk_body(const double* __restrict__ T, const double* __restrict__ ws,
                                                  const double* __restrict__ rs, int Sd, const int (&offA)[kTNBW],
-                                                 const int (&offB)[kTNBW], double (&C)[kTNBW][2][4][2],
+                                                 const int (&offB)[kTNBW], bool has_g, double (&C)[kTNBW][2][4][2],
                                                  double (&gacc)[4]) {
     constexpr int N0 = pat_n0(PAT), N1 = pat_n1(PAT);
 #pragma unroll 1
@@ -125,7 +125,7 @@ __device__ __forceinline__ void tiled_chunk_body(const double* __restrict__ T, c
                 if (jj < N0) dmma884(C[b][0][jj][0], C[b][0][jj][1], a0, f[jj]);
                 if (jj < N1) dmma884(C[b][1][jj][0], C[b][1][jj][1], a1, f[jj]);
             }
-            if (HASG) {
+            if (HASG && has_g) {  // has_g: run-time owner flag (GLM instantiation, see the dispatch below)
                 const double rv = rs[4 * ks];
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) gacc[jj] = fma(rv, f[jj], gacc[jj]);
@@ -358,7 +358,11 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
         // this warp's (number of full blocks, shape of the partial block).  The bodies are straight-line code with
         // unconditional fragment loads (every column a block can name exists in shared memory); sharing the rest
         // keeps the instruction footprint of the 12 MMA warps inside the 32 KB instruction cache.
-        const int path = pat * 8 + (has_g ? 4 : 0) + nfull;
+        // Linear family: owners and non-owners run different bodies (same-run A/B, 5e7 rows x p=100: 23.35 -> 21.70 ms).
+        // GLM family: every warp runs the owner body with the run-time flag — the compiled-out variant measured SLOWER
+        // there (p=100 fused link 25.4 -> 27.3 ms, p=500 28.3 -> 29.2 ms; only p=182 gained, 23.6 -> 22.1), so it keeps
+        // the round-1 code; profiles/r02_k1_tiled_ab.md.
+        const int path = pat * 8 + ((LOGIT || has_g) ? 4 : 0) + nfull;
         int st = 0;
         uint32_t par = 0;
         for (int ci = 0; ci < my_n; ci++) {
@@ -368,8 +372,8 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
             const double* ws = ws_all + st * kTCH + q;
             const double* rs = rs_all + st * kTCH + q;
 #define DLSA_BODY(NF_, PAT_)                                                                                     \
-    case (PAT_) * 8 + (NF_): tiled_chunk_body<LOGIT, NF_, PAT_, kTCH / 16, false>(T, ws, rs, Sd, offA, offB, C, gacc); break; \
-    case (PAT_) * 8 + 4 + (NF_): tiled_chunk_body<LOGIT, NF_, PAT_, kTCH / 16, true>(T, ws, rs, Sd, offA, offB, C, gacc); break;
+    case (PAT_) * 8 + (NF_): tiled_chunk_body<LOGIT, NF_, PAT_, kTCH / 16, false>(T, ws, rs, Sd, offA, offB, false, C, gacc); break; \
+    case (PAT_) * 8 + 4 + (NF_): tiled_chunk_body<LOGIT, NF_, PAT_, kTCH / 16, true>(T, ws, rs, Sd, offA, offB, has_g, C, gacc); break;
             switch (path) {
                 DLSA_BODY(0, kPatNone) DLSA_BODY(1, kPatNone) DLSA_BODY(2, kPatNone) DLSA_BODY(3, kPatNone)
                 DLSA_BODY(0, kPat34) DLSA_BODY(1, kPat34) DLSA_BODY(2, kPat34)

@@ -16,7 +16,7 @@ constexpr int kCholSmemMaxP = 160;  // p*p*8 <= 204,800 B fits one CTA's shared 
 
 // In-place Cholesky A = L L' on the lower triangle of L[p][ld] (right-looking, one CTA), then
 // x = A^-1 b by forward/back substitution.  Returns false (in *ok_s) if a pivot is not positive/finite.
-__device__ void chol_solve_cta(double* L, int ld, int p, double* x, int* ok_s) {
+__device__ __forceinline__ void chol_solve_cta(double* L, int ld, int p, double* x, int* ok_s) {
     const int tid = threadIdx.x, nt = blockDim.x;
     if (tid == 0) *ok_s = 1;
     __syncthreads();
@@ -61,56 +61,140 @@ __device__ void chol_solve_cta(double* L, int ld, int p, double* x, int* ok_s) {
 }
 
 
-// ---- p > 160: the factor does not fit shared memory; blocked right-looking Cholesky on the copy in global memory ------
-// Panels of 32 columns: (1) the 32x32 diagonal block is factored in shared memory by one warp, (2) every row below
-// solves its 32-column slice against it (one thread per row, the row in registers) and leaves it in a shared-memory
-// panel P, (3) the trailing lower triangle gets  A22 -= P P'  as 8x8 tiles on DMMA (mma.sync m8n8k4 f64; fragments from
-// P with a conflict-free pitch, C tiles straight from / to global memory, kTIF independent tiles in flight per warp).
-// 2/3 of the flops of a p=500 factorisation are step (3).  The unblocked rank-1 version this replaces took 68 ms for
-// 1024 matrices of p=500 (C5); see profiles/r01_c5_breakdown.md.
+// ---- p > 160: the factor does not fit shared memory; blocked LEFT-looking Cholesky on the copy in global memory -------
+// Panels of 32 columns.  For panel kb the 16 warps each take 32-row blocks of the panel and form
+//     U = A[rows, kb:kb+32] - L[rows, 0:kb] L[kb:kb+32, 0:kb]'
+// as 4x4 tiles of 8x8 on DMMA with the 16 accumulator tiles in registers for the whole k loop (fragments straight from
+// global memory, 16 bytes per lane = two k-steps per load, the next load issued before the current MMAs), then leave U in a
+// shared-memory panel P.  The 32x32 diagonal block of P is factored by one warp, every row below solves its 32-column
+// slice against it (one thread per row, the row in registers) and the finished columns go back to global memory.
+// Unlike the right-looking form this replaces (profiles/r01_k2_chol_p500_ncu_summary.csv: DMMA pipe 10 % busy, the warps
+// waiting on the read-modify-write of the trailing matrix in global memory and on CTA barriers), no element of the
+// trailing matrix is touched before its own panel: every entry of A is read once and every entry of L written once.
 constexpr int kNB = 32;
 constexpr int kDPitch = 33;
-constexpr int kTIF = 8;      // 8x8 tiles in flight per warp in the trailing update (independent C loads and DMMA chains)
-constexpr int kPPitch = 36;  // == 4 (mod 16) doubles: the (row a8, column q) fragment loads hit 16 distinct banks per half-warp
+constexpr int kPPitch = 36;  // == 4 (mod 16) doubles: 16-byte aligned rows, (row a8, column pair q) stores spread over the banks
 
-__device__ void chol_blocked_cta(double* L, int ld, int p, double* x, double* sm, int* ok_s) {
-    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
+__device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, double* L, int ld, int p, double* x,
+                                                 double* sm, int* ok_s) {
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
     const int a8 = lane >> 2, q = lane & 3;
     double* D = sm;
     double* invd = D + kNB * kDPitch;
-    double* P = invd + kNB;
+    double* W = invd + kNB;                 // inverse of the diagonal block's factor, [32][kPPitch]
+    double* P = W + kNB * kPPitch;
     if (tid == 0) *ok_s = 1;
     __syncthreads();
     for (int kb = 0; kb < p; kb += kNB) {
         const int nb = (p - kb < kNB) ? (p - kb) : kNB;
-        const int m = p - kb - nb;            // rows below the panel
-        const int mpad = (m + 7) & ~7;
-        // (1) diagonal block -> shared memory (identity beyond nb), factored by warp 0
+        const int rows_total = p - kb;                 // rows of the panel, the diagonal block first
+        const int nrb = (rows_total + 31) >> 5;
+        // (1) panel update on DMMA: 32 rows x 32 columns per warp and turn, k over the finished columns 0..kb-1
+        for (int b = warp; b < nrb; b += nwarps) {
+            const int r0 = kb + 32 * b;
+            double c0[4][4], c1[4][4];
+#pragma unroll
+            for (int ti = 0; ti < 4; ti++)
+#pragma unroll
+                for (int tj = 0; tj < 4; tj++) { c0[ti][tj] = 0.0; c1[ti][tj] = 0.0; }
+            int ao[4], bo[4];
+            bool aok[4], bok[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int ra = r0 + 8 * t + a8, rb = kb + 8 * t + a8;
+                aok[t] = ra < p;
+                bok[t] = rb < p;
+                ao[t] = (aok[t] ? ra : p - 1) * ld + 2 * q;
+                bo[t] = (bok[t] ? rb : p - 1) * ld + 2 * q;
+            }
+#pragma unroll 1
+            for (int kk = 0; kk < kb; kk += 8) {
+                double2 ac[4], bc[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    ac[t] = *reinterpret_cast<const double2*>(L + ao[t] + kk);
+                    bc[t] = *reinterpret_cast<const double2*>(L + bo[t] + kk);
+                    if (!aok[t]) ac[t] = make_double2(0.0, 0.0);
+                    if (!bok[t]) bc[t] = make_double2(0.0, 0.0);
+                }
+                // lane q carries columns kk + 2q (.x) and kk + 2q + 1 (.y) of BOTH operands: two k-steps whose k order is
+                // a permutation of kk..kk+7 — the sum over k does not care
+#pragma unroll
+                for (int ti = 0; ti < 4; ti++)
+#pragma unroll
+                    for (int tj = 0; tj < 4; tj++) {
+                        dmma884(c0[ti][tj], c1[ti][tj], ac[ti].x, bc[tj].x);
+                        dmma884(c0[ti][tj], c1[ti][tj], ac[ti].y, bc[tj].y);
+                    }
+            }
+            // U = A - (L L')  ->  P; entries above the diagonal of the diagonal block are never read
+#pragma unroll
+            for (int ti = 0; ti < 4; ti++) {
+                const int r = r0 + 8 * ti + a8;
+#pragma unroll
+                for (int tj = 0; tj < 4; tj++) {
+                    const int c = kb + 8 * tj + 2 * q;
+                    double v0 = 0.0, v1 = 0.0;
+                    if (r < p) {   // the entries of A are read here, once; L only ever holds finished columns
+                        if (c < kb + nb && c <= r) v0 = A[(size_t)r * p + c] - c0[ti][tj];
+                        if (c + 1 < kb + nb && c + 1 <= r) v1 = A[(size_t)r * p + c + 1] - c1[ti][tj];
+                    }
+                    *reinterpret_cast<double2*>(P + (size_t)(32 * b + 8 * ti + a8) * kPPitch + 8 * tj + 2 * q) =
+                        make_double2(v0, v1);
+                }
+            }
+        }
+        __syncthreads();
+        // (2) diagonal block (rows 0..31 of P) -> D (identity beyond nb), factored by warp 0
         for (int e = tid; e < kNB * kNB; e += nt) {
             const int r = e >> 5, c = e & 31;
             double v = (r == c) ? 1.0 : 0.0;
-            if (r < nb && c <= r) v = L[(size_t)(kb + r) * ld + kb + c];
+            if (r < nb && c <= r) v = P[r * kPPitch + c];
             D[r * kDPitch + c] = v;
         }
         __syncthreads();
         if (warp == 0) {
+            // lane i holds row i of the block in registers; column j of the factor travels by shuffle
+            double row[kNB];
+#pragma unroll
+            for (int c = 0; c < kNB; c++) row[c] = D[lane * kDPitch + c];
             bool good = true;
+#pragma unroll
             for (int j = 0; j < kNB; j++) {
-                const double d = D[j * kDPitch + j];
-                if (!(d > 0.0) || !isfinite(d)) { good = false; break; }  // warp-uniform
-                const double dj = sqrt(d);
-                const double lr = (lane > j) ? D[lane * kDPitch + j] / dj : 0.0;
-                __syncwarp();
-                if (lane == j) D[j * kDPitch + j] = dj;
-                if (lane > j) D[lane * kDPitch + j] = lr;
-                __syncwarp();
-                if (lane > j)
-                    for (int c = j + 1; c <= lane; c++)
-                        D[lane * kDPitch + c] = fma(-lr, D[c * kDPitch + j], D[lane * kDPitch + c]);
-                __syncwarp();
+                const double d = __shfl_sync(0xffffffffu, row[j], j);
+                good = good && (d > 0.0) && isfinite(d);
+                const double rs = rsqrt(d);                          // one reciprocal square root instead of sqrt + divide on the
+                const double lj = row[j] * rs;                       // 32-step dependent chain: column j of the factor (lane j: d/sqrt(d))
+                row[j] = lj;
+#pragma unroll
+                for (int c = j + 1; c < kNB; c++) {
+                    const double lc = __shfl_sync(0xffffffffu, lj, c);
+                    row[c] = fma(-lj, lc, row[c]);   // only c <= lane is ever read; the rest is harmless garbage
+                }
             }
-            if (good) invd[lane] = 1.0 / D[lane * kDPitch + lane];
-            else if (lane == 0) *ok_s = 0;
+            if (good) {
+#pragma unroll
+                for (int c = 0; c < kNB; c++) D[lane * kDPitch + c] = row[c];
+                // M = L11^-1 (lower triangular), lane j owns column j in registers:
+                //   M[i][j] = -(sum_{t=j}^{i-1} L11[i][t] M[t][j]) / L11[i][i];  L11[i][t] comes from lane i by shuffle
+                double m[kNB];
+                const double dinv = 1.0 / row[lane];
+                invd[lane] = dinv;
+#pragma unroll
+                for (int i = 0; i < kNB; i++) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int t = 0; t < i; t++) {
+                        const double lit = __shfl_sync(0xffffffffu, row[t], i);
+                        if (t & 1) s1 = fma(lit, m[t], s1); else s0 = fma(lit, m[t], s0);
+                    }
+                    const double di = __shfl_sync(0xffffffffu, dinv, i);
+                    m[i] = (lane == i) ? dinv : ((lane < i) ? -(s0 + s1) * di : 0.0);
+                    W[i * kPPitch + lane] = m[i];
+                }
+            } else if (lane == 0) {
+                *ok_s = 0;
+            }
         }
         __syncthreads();
         if (*ok_s == 0) return;
@@ -118,79 +202,46 @@ __device__ void chol_blocked_cta(double* L, int ld, int p, double* x, double* sm
             const int r = e >> 5, c = e & 31;
             if (r < nb && c <= r) L[(size_t)(kb + r) * ld + kb + c] = D[r * kDPitch + c];
         }
-        if (m == 0) break;
-        // (2) panel: row i solves  x L11' = a  (forward substitution over the 32 columns), x -> global and P
-        for (int ri = tid; ri < mpad; ri += nt) {
-            double xr[kNB];
-            if (ri < m) {
-                double* row = L + (size_t)(kb + nb + ri) * ld + kb;
+        // (3) panel rows below the diagonal block:  X = U L11^-T = U M'  — one more 32-wide GEMM on DMMA per 32-row block
+        //     (A fragments from P, B[k][n] = M[n][k] from W), straight to global memory
+        for (int b = 1 + warp; b < nrb; b += nwarps) {
+            double c0[4][4], c1[4][4];
 #pragma unroll
-                for (int c = 0; c < kNB; c++) xr[c] = (c < nb) ? row[c] : 0.0;
+            for (int ti = 0; ti < 4; ti++)
 #pragma unroll
-                for (int c = 0; c < kNB; c++) {
-                    double sacc = xr[c];
-#pragma unroll
-                    for (int t = 0; t < c; t++) sacc = fma(-xr[t], D[c * kDPitch + t], sacc);
-                    xr[c] = sacc * invd[c];
-                }
-#pragma unroll
-                for (int c = 0; c < kNB; c++)
-                    if (c < nb) row[c] = xr[c];
-            } else {
-#pragma unroll
-                for (int c = 0; c < kNB; c++) xr[c] = 0.0;
-            }
-#pragma unroll
-            for (int c = 0; c < kNB; c++) P[ri * kPPitch + c] = xr[c];
-        }
-        __syncthreads();
-        // (3) trailing update on DMMA: tile (ti, tc), tc <= ti, rows kb+nb+8ti.., columns kb+nb+8tc..
-        const int mt = mpad >> 3;
-        const int ntile = mt * (mt + 1) / 2;
-        const int base = kb + nb;
-        for (int t0 = warp * kTIF; t0 < ntile; t0 += (nt >> 5) * kTIF) {
-            double c0[kTIF], c1[kTIF];
-            int gi[kTIF], gc[kTIF], pi[kTIF], pc[kTIF];
-            bool in0[kTIF], in1[kTIF];
-#pragma unroll
-            for (int u = 0; u < kTIF; u++) {
-                const int t = t0 + u;
-                int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-                while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-                while (ti * (ti + 1) / 2 > t) ti--;
-                const int tc = t - ti * (ti + 1) / 2;
-                const bool live = t < ntile;
-                pi[u] = (live ? 8 * ti : 0) + a8;
-                pc[u] = (live ? 8 * tc : 0) + a8;
-                gi[u] = base + (live ? 8 * ti : 0) + a8;
-                gc[u] = base + (live ? 8 * tc : 0) + 2 * q;
-                in0[u] = live && gi[u] < p && gc[u] <= gi[u];
-                in1[u] = live && gi[u] < p && gc[u] + 1 <= gi[u];
-                c0[u] = in0[u] ? L[(size_t)gi[u] * ld + gc[u]] : 0.0;
-                c1[u] = in1[u] ? L[(size_t)gi[u] * ld + gc[u] + 1] : 0.0;
-            }
-#pragma unroll
+                for (int tj = 0; tj < 4; tj++) { c0[ti][tj] = 0.0; c1[ti][tj] = 0.0; }
+            const double* Pa = P + (size_t)(32 * b + a8) * kPPitch + q;
+            const double* Wb = W + (size_t)a8 * kPPitch + q;
+#pragma unroll 2
             for (int kk = 0; kk < kNB; kk += 4) {
+                double av[4], bv[4];
 #pragma unroll
-                for (int u = 0; u < kTIF; u++) {
-                    const double av = -P[pi[u] * kPPitch + kk + q];
-                    const double bv = P[pc[u] * kPPitch + kk + q];
-                    dmma884(c0[u], c1[u], av, bv);
+                for (int t = 0; t < 4; t++) {
+                    av[t] = Pa[(size_t)(8 * t) * kPPitch + kk];
+                    bv[t] = Wb[(size_t)(8 * t) * kPPitch + kk];
+                }
+#pragma unroll
+                for (int ti = 0; ti < 4; ti++)
+#pragma unroll
+                    for (int tj = 0; tj < 4; tj++) dmma884(c0[ti][tj], c1[ti][tj], av[ti], bv[tj]);
+            }
+#pragma unroll
+            for (int ti = 0; ti < 4; ti++) {
+                const int r = kb + 32 * b + 8 * ti + a8;
+                if (r < p) {
+#pragma unroll
+                    for (int tj = 0; tj < 4; tj++)
+                        *reinterpret_cast<double2*>(L + (size_t)r * ld + kb + 8 * tj + 2 * q) = make_double2(c0[ti][tj], c1[ti][tj]);
                 }
             }
-#pragma unroll
-            for (int u = 0; u < kTIF; u++) {
-                if (in0[u]) L[(size_t)gi[u] * ld + gc[u]] = c0[u];
-                if (in1[u]) L[(size_t)gi[u] * ld + gc[u] + 1] = c1[u];
-            }
         }
-        __syncthreads();
+        __syncthreads();   // the finished columns are in global memory before the next panel reads them
     }
 }
 
 // x = (L L')^-1 x with the factor in global memory: blocked forward and backward substitution (diagonal block solved by
 // warp 0 with the lane's row / column of the block in registers, the rest of x updated by all threads)
-__device__ void chol_blocked_solve_cta(const double* L, int ld, int p, double* x) {
+__device__ __forceinline__ void chol_blocked_solve_cta(const double* L, int ld, int p, double* x) {
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
     __syncthreads();  // the last diagonal block was written back by all threads
     for (int kb = 0; kb < p; kb += kNB) {  // forward: L z = b
@@ -265,20 +316,22 @@ __global__ void __launch_bounds__(SMEM ? kCholThreads : kCholThreadsBlocked) cho
         L = xs + ((p + 1) & ~1);
         ld = p | 1;  // odd leading dimension: column walks hit distinct banks
     } else {
-        L = gws + (size_t)k * p * p;
-        ld = p;
+        ld = (p + 1) & ~1;  // even: every row of the factor starts 16-byte aligned (two doubles per fragment load)
+        L = gws + (size_t)k * p * ld;
     }
     const double* Ak = A + (size_t)k * p * p;
-    for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
-        const int i = e / p, c = e - i * p;
-        if (c <= i) L[(size_t)i * ld + c] = Ak[e];
+    if (SMEM) {
+        for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
+            const int i = e / p, c = e - i * p;
+            if (c <= i) L[(size_t)i * ld + c] = Ak[e];
+        }
     }
     for (int i = threadIdx.x; i < p; i += blockDim.x) xs[i] = b[(size_t)k * p + i];
     __syncthreads();
     if (SMEM) {
         chol_solve_cta(L, ld, p, xs, &ok_s);
     } else {
-        chol_blocked_cta(L, ld, p, xs, xs + ((p + 1) & ~1), &ok_s);
+        chol_blocked_cta(Ak, L, ld, p, xs, xs + ((p + 1) & ~1), &ok_s);
         if (ok_s != 0) chol_blocked_solve_cta(L, ld, p, xs);
     }
     const bool ok = ok_s != 0;
@@ -331,7 +384,7 @@ __global__ void __launch_bounds__(SMEM ? kCholThreads : kCholThreadsBlocked) cho
 static size_t chol_smem_bytes(int p) { return ((size_t)((p + 1) & ~1) + (size_t)p * (p | 1)) * sizeof(double); }
 
 size_t chol_workspace_bytes(int K, int p) {
-    return p <= kCholSmemMaxP ? 0 : (size_t)K * p * p * sizeof(double);
+    return p <= kCholSmemMaxP ? 0 : (size_t)K * p * ((p + 1) & ~1) * sizeof(double);
 }
 
 int chol_launch(const double* A, const double* b, int K, int p, int mode, double* beta, double* x_out,
@@ -347,8 +400,9 @@ int chol_launch(const double* A, const double* b, int K, int p, int mode, double
         const size_t need = chol_workspace_bytes(K, p);
         DLSA_REQUIRE(workspace != nullptr && workspace_bytes >= need, DLSA_E_WORKSPACE,
                      "cholesky: workspace too small (%zu < %zu)", workspace_bytes, need);
-        const int mmax = (p > kNB) ? ((p - kNB + 7) & ~7) : 8;
-        const size_t smem = ((size_t)((p + 1) & ~1) + (size_t)kNB * kDPitch + kNB + (size_t)mmax * kPPitch) * sizeof(double);
+        const int prow = (p + 31) & ~31;   // the panel holds every row from the diagonal block down, in 32-row blocks
+        const size_t smem = ((size_t)((p + 1) & ~1) + (size_t)kNB * kDPitch + kNB + (size_t)kNB * kPPitch +
+                             (size_t)prow * kPPitch) * sizeof(double);
         DLSA_CUDA(cudaFuncSetAttribute(chol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         chol_kernel<false><<<K, kCholThreadsBlocked, smem, st>>>(A, b, K, p, mode, beta, x_out, max_delta, status, active,
                                                           iters, n_active, tol, damp_above, damp_factor,
