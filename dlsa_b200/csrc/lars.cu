@@ -5,8 +5,13 @@
 // first-argmin selection of dlsa() (dlsa/dlsa.py:90-91).
 //
 // The path is sequential (each knot depends on the previous one), so K6 is ONE persistent CTA: the O(m a)
-// correlation update runs on all threads against the L2-resident scaled Sigma, the triangular solves on the
-// upper Cholesky factor R (packed rows, shared memory when it fits) run on warp 0 with shuffles.
+// correlation update runs on all threads against the L2-resident scaled Sigma.  Until a lasso drop happens nothing in
+// the step is a sequential triangular solve: besides the upper Cholesky factor R the kernel keeps R^-1 (packed like R),
+// z = R^-T Sign and G = R^-1 z, and appending a variable is two triangular MATRIX-VECTOR products on all threads
+// (v = R^-T x_old, the new column of R; c = -R^-1 v / r_pp, the new column of R^-1) plus O(a) updates of z and G —
+// the reference's updateR / backsolve chain (dlsa/lsa.py:12-32,151) computes the same vectors by substitution.
+// After the first drop (Givens deletion on R, dlsa/lsa.py:35-71) the step falls back to blocked triangular solves on R
+// (diagonal blocks on warp 0 with shuffles, the rest on all threads).
 // K7 evaluates the quadratic form of every knot in parallel (one CTA per knot) and K7b picks the minima.
 #include "common.cuh"
 
@@ -18,7 +23,7 @@ constexpr int kLarsRSmemDoubles = 16384;  // packed R kept in shared memory up t
 
 struct LarsShared {
     double Cmax, A, gamhat, zmin, red[kLarsThreads / 32];
-    int n_act, n_join, k, drops_pending, any_drop, err;
+    int n_act, n_join, k, drops_pending, any_drop, err, fast;
     int ired[kLarsThreads / 32];
 };
 
@@ -231,6 +236,7 @@ struct LarsArgs {
     int* info;
     double* Sig;   // workspace [m*m] scaled Sigma
     double* Rg;    // workspace packed R when it does not fit in shared memory
+    double* Rinv;  // workspace packed R^-1 (same layout)
     double* scal;  // workspace [4]: a11, beta0_init, (unused)
 };
 
@@ -248,11 +254,14 @@ __global__ void __launch_bounds__(kLarsThreads, 1) lars_path_kernel(const LarsAr
     double* tmp = Sign + m;     // triangular-solve scratch
     double* sgn = tmp + m;      // sign(b)
     double* absb = sgn + m;
-    int* act = reinterpret_cast<int*>(absb + m);
+    double* zf = absb + m;      // R^-T Sign, kept up to date as columns are appended (one O(a) update per join instead of
+                                // an O(a^2) forward solve per step); rebuilt after a lasso drop
+    double* gi = zf + m;        // G = R^-1 z (the un-normalised equiangular direction), maintained while sh.fast
+    int* act = reinterpret_cast<int*>(gi + m);
     int* state = act + m;       // 0 inactive, 1 active, 2 ignored
     int* joiners = state + m;
     unsigned char* dropflag = reinterpret_cast<unsigned char*>(joiners + m);
-    double* Rs = reinterpret_cast<double*>(smem_raw + ((size_t)(7 * m) * 8 + (size_t)(3 * m) * 4 + m + 15) / 16 * 16);
+    double* Rs = reinterpret_cast<double*>(smem_raw + ((size_t)(9 * m) * 8 + (size_t)(3 * m) * 4 + m + 15) / 16 * 16);
     const bool r_in_smem = (size_t)m * (m + 1) / 2 <= kLarsRSmemDoubles;
     double* R = r_in_smem ? Rs : a.Rg;
 
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(kLarsThreads, 1) lars_path_kernel(const LarsAr
         Cvec[j] = c;
         a.beta_path[j] = 0.0;
     }
-    if (tid == 0) { sh.n_act = 0; sh.k = 0; sh.drops_pending = 0; sh.err = 0; }
+    if (tid == 0) { sh.n_act = 0; sh.k = 0; sh.drops_pending = 0; sh.err = 0; sh.fast = 1; }
     __syncthreads();
 
     const int max_steps = a.max_steps;
@@ -334,6 +343,9 @@ __global__ void __launch_bounds__(kLarsThreads, 1) lars_path_kernel(const LarsAr
                         R[0] = nx;
                         act[0] = inew; state[inew] = 1;
                         Sign[0] = (Cvec[inew] > 0.0) ? 1.0 : ((Cvec[inew] < 0.0) ? -1.0 : 0.0);
+                        zf[0] = Sign[0] / nx;
+                        a.Rinv[0] = 1.0 / nx;
+                        gi[0] = zf[0] / nx;
                         sh.n_act = 1;
                     }
                     __syncthreads();
@@ -341,10 +353,31 @@ __global__ void __launch_bounds__(kLarsThreads, 1) lars_path_kernel(const LarsAr
                 }
                 for (int l = tid; l < na; l += nt) tmp[l] = a.Sig[(size_t)inew * m + act[l]];
                 __syncthreads();
-                forward_solve(R, na, m, tmp);  // updateR: r = backsolvet(R, xold)  (:19)
-                double part = 0.0;
-                for (int l = tid; l < na; l += nt) part = fma(tmp[l], tmp[l], part);
+                const bool fast = sh.fast != 0;
+                if (fast) {  // updateR: r = backsolvet(R, xold) (:19) as the product R^-T xold; thread i owns entry i
+                    for (int i = tid; i < na; i += nt) {
+                        double acc0 = 0.0, acc1 = 0.0;
+                        int l = 0;
+                        for (; l + 1 <= i; l += 2) {
+                            acc0 = fma(a.Rinv[rpk(l, i, m)], tmp[l], acc0);
+                            acc1 = fma(a.Rinv[rpk(l + 1, i, m)], tmp[l + 1], acc1);
+                        }
+                        if (l <= i) acc0 = fma(a.Rinv[rpk(l, i, m)], tmp[l], acc0);
+                        u[i] = acc0 + acc1;
+                    }
+                    __syncthreads();
+                    for (int i = tid; i < na; i += nt) tmp[i] = u[i];
+                    __syncthreads();
+                } else {
+                    forward_solve(R, na, m, tmp);
+                }
+                double part = 0.0, part2 = 0.0;
+                for (int l = tid; l < na; l += nt) {
+                    part = fma(tmp[l], tmp[l], part);
+                    part2 = fma(tmp[l], zf[l], part2);   // new column of R against R^-T Sign
+                }
                 const double ss = block_sum(part, sh.red);
+                const double rz = block_sum(part2, sh.red);
                 double rpp = nx * nx - ss;  // (:20)
                 if (rpp <= eps) {
                     // machine-singular: back out and ignore the variable (:138-143; R :168-173)
@@ -352,10 +385,33 @@ __global__ void __launch_bounds__(kLarsThreads, 1) lars_path_kernel(const LarsAr
                 } else {
                     rpp = sqrt(rpp);
                     for (int l = tid; l < na; l += nt) R[rpk(l, na, m)] = tmp[l];
+                    const double sgn_new = (Cvec[inew] > 0.0) ? 1.0 : ((Cvec[inew] < 0.0) ? -1.0 : 0.0);
+                    const double z_new = (sgn_new - rz) / rpp;   // last row of the forward substitution R' z = Sign
+                    if (fast) {
+                        // new column of R^-1: c = -R^-1 r / r_pp, one warp per row (row l of R^-1 is contiguous), and
+                        // G <- [G + c z_new ; z_new / r_pp]
+                        const int wrp = tid >> 5, lane = tid & 31;
+                        for (int l = wrp; l < na; l += (nt >> 5)) {
+                            const double* rrow = a.Rinv + rpk(l, l, m);
+                            double acc = 0.0;
+                            for (int i = l + lane; i < na; i += 32) acc = fma(rrow[i - l], tmp[i], acc);
+                            for (int sft = 16; sft >= 1; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+                            if (lane == 0) {
+                                const double cl = -acc / rpp;
+                                a.Rinv[rpk(l, na, m)] = cl;
+                                gi[l] = fma(cl, z_new, gi[l]);
+                            }
+                        }
+                    }
                     if (tid == 0) {
                         R[rpk(na, na, m)] = rpp;
                         act[na] = inew; state[inew] = 1;
-                        Sign[na] = (Cvec[inew] > 0.0) ? 1.0 : ((Cvec[inew] < 0.0) ? -1.0 : 0.0);
+                        Sign[na] = sgn_new;
+                        zf[na] = z_new;
+                        if (fast) {
+                            a.Rinv[rpk(na, na, m)] = 1.0 / rpp;
+                            gi[na] = z_new / rpp;
+                        }
                         sh.n_act = na + 1;
                     }
                 }
@@ -369,10 +425,14 @@ __global__ void __launch_bounds__(kLarsThreads, 1) lars_path_kernel(const LarsAr
             break;
         }
         // equiangular direction: Gi1 = R^-1 R^-T Sign, A = 1/sqrt(Gi1.Sign), w = A Gi1 (:151-153)
-        for (int l = tid; l < na; l += nt) tmp[l] = Sign[l];
-        __syncthreads();
-        forward_solve(R, na, m, tmp);
-        backward_solve(R, na, m, tmp);
+        if (sh.fast) {
+            for (int l = tid; l < na; l += nt) tmp[l] = gi[l];   // == R^-1 R^-T Sign
+            __syncthreads();
+        } else {
+            for (int l = tid; l < na; l += nt) tmp[l] = zf[l];   // == R^-T Sign
+            __syncthreads();
+            backward_solve(R, na, m, tmp);
+        }
         double part = 0.0;
         for (int l = tid; l < na; l += nt) part = fma(tmp[l], Sign[l], part);
         const double gs = block_sum(part, sh.red);
@@ -438,6 +498,13 @@ __global__ void __launch_bounds__(kLarsThreads, 1) lars_path_kernel(const LarsAr
                     __syncthreads();
                 }
             }
+        }
+        if (drop_now) {  // columns were deleted from R: from here on substitution on R; rebuild R^-T Sign for the shrunken factor
+            if (tid == 0) sh.fast = 0;
+            const int na3 = sh.n_act;
+            for (int l = tid; l < na3; l += nt) zf[l] = Sign[l];
+            __syncthreads();
+            if (na3 > 0) forward_solve(R, na3, m, zf);
         }
         if (tid == 0) sh.drops_pending = drop_now ? 1 : 0;
         __syncthreads();
@@ -517,12 +584,12 @@ __global__ void lars_select_kernel(const LarsArgs a) {
     }
 }
 
-static size_t lars_vec_bytes(int m) { return ((size_t)(7 * m) * 8 + (size_t)(3 * m) * 4 + m + 15) / 16 * 16; }
+static size_t lars_vec_bytes(int m) { return ((size_t)(9 * m) * 8 + (size_t)(3 * m) * 4 + m + 15) / 16 * 16; }
 
 size_t lars_workspace_bytes(int p0, int max_steps) {
     (void)max_steps;
     const size_t m = (size_t)p0;
-    return (m * m + m * (m + 1) / 2 + 8) * sizeof(double);
+    return (m * m + 2 * (m * (m + 1) / 2) + 8) * sizeof(double);
 }
 
 int lars_launch(const double* Sigma0, const double* b0, int p0, int intercept, double n, int type, double eps,
@@ -541,6 +608,7 @@ int lars_launch(const double* Sigma0, const double* b0, int p0, int intercept, d
     a.scal = ws;
     a.Sig = ws + 8;
     a.Rg = a.Sig + (size_t)p0 * p0;
+    a.Rinv = a.Rg + (size_t)p0 * (p0 + 1) / 2;
     const bool r_in_smem = (size_t)m * (m + 1) / 2 <= kLarsRSmemDoubles;
     const size_t smem = lars_vec_bytes(m) + (r_in_smem ? (size_t)m * (m + 1) / 2 * 8 : 0);
     DLSA_CUDA(cudaFuncSetAttribute(lars_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
