@@ -219,3 +219,28 @@ def test_facade_compact_route_equals_dense_route(eng, monkeypatch):
     assert relfro(compact.iloc[:, 3:].to_numpy(), dense.iloc[:, 3:].to_numpy()) < 1e-10
     p = one.shape[0]
     assert np.max(np.abs(one["coef"].to_numpy() - compact["coef"].to_numpy()[p:2 * p])) < 1e-8
+
+
+def test_host_entry_for_the_compact_design_matches_the_device_entry(eng):
+    """dlsa_fit_host_cat: host-resident compact design (pinned or pageable), partition blocks copied on a copy stream while
+    earlier blocks are fitted — same estimates as fitting the device-resident design in one batch."""
+    from dlsa_b200 import synth
+    n, K = 400_000, 80
+    num, codes, n_levels, y = synth.airline_shaped_device(n, 3, torch.device("cuda"))
+    n_levels = [11, 6, 7, 12, 12]
+    codes = codes.clone()
+    for c, L in enumerate(n_levels):
+        codes[:, c] = torch.where(codes[:, c] >= L, torch.full_like(codes[:, c], -1), codes[:, c])
+    off = synth.equal_partition_offsets(n, K, torch.device("cuda"))
+    fits = eng.fit_logistic_partitions_cat(num, codes, n_levels, y, off, fit_intercept=True)
+    f0, c0, p0 = eng.finish_fit(fits, True, float(n))
+    for pinned in (True, False):
+        nh, ch, yh = num.cpu(), codes.cpu(), y.cpu()
+        if pinned:
+            nh, ch, yh = nh.pin_memory(), ch.pin_memory(), yh.pin_memory()
+        f1, c1, p1 = eng.dlsa_fit_host_cat(nh, ch, n_levels, yh, off.cpu(), fit_intercept=True, sample_size=float(n), n_groups=4)
+        assert int(f1.status.abs().sum()) == 0
+        assert (f1.coef - f0.coef).abs().max().item() < 1e-9
+        assert float((f1.Sig_inv - f0.Sig_inv).norm() / f0.Sig_inv.norm()) < 1e-10
+        assert (c1.beta_byOLS - c0.beta_byOLS).abs().max().item() < 1e-9
+        assert p1.argmin_BIC == p0.argmin_BIC and torch.equal(p1.beta[p1.argmin_BIC] != 0, p0.beta[p0.argmin_BIC] != 0)

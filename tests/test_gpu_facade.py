@@ -268,3 +268,81 @@ def test_model_eval_and_data_info_against_reference_goldens():
     lc = logistic_model_eval(dfc, "y", par_c, fit_intercept=True, dummy_info=info, dummy_factors_baseline=base,
                              data_info=dinfo_c)
     assert np.allclose(lc.to_numpy()[0], g["c_ref_loglik"], rtol=1e-10)
+
+
+def test_ingest_csv_matches_the_pandas_facade(tmp_path):
+    """f-3: CSV -> Arrow -> device codes / numerics (ingest.ingest + ingest.fit) gives the frames, the dummy_info and the
+    describe() statistics the pandas route gives (dlsa.dummies.* + describe + logistic_model_partitions); the label rule
+    (ArrDelay > 0), dropna and partition_id = row % K follow projects/logistic_dlsa.py:218-237."""
+    from dlsa_b200 import dummies, ingest, models
+    rng = np.random.default_rng(44)
+    n = 9000
+    df = pd.DataFrame({"Year": rng.integers(1987, 2009, n).astype(float), "Distance": rng.gamma(2.0, 400.0, n),
+                       "DepTime": rng.uniform(0, 2400, n),
+                       "Month": rng.integers(1, 13, n),
+                       "UniqueCarrier": rng.choice(list("ABCDEFGH"), size=n, p=np.array([30, 20, 15, 12, 10, 6, 4, 3]) / 100)})
+    eta = -0.2 + 0.002 * (df["Distance"] - 800) / 4 + 0.3 * (df["UniqueCarrier"] == "B") - 0.2 * (df["Month"] == 7)
+    df["ArrDelay"] = np.where(rng.random(n) < 1 / (1 + np.exp(-eta)), rng.uniform(1, 90, n), -rng.uniform(0, 30, n))
+    df.loc[rng.choice(n, 37, replace=False), "DepTime"] = np.nan          # rows dropna() must remove
+    path = tmp_path / "airline_like.csv"
+    df.to_csv(path, index=False)
+    usecols_x = ["Year", "Distance", "DepTime", "Month", "UniqueCarrier"]
+    des = ingest.ingest(str(path), usecols_x, "ArrDelay", dummy_columns=["Month", "UniqueCarrier"], dummy_keep_top=[1, 0.8],
+                        dummy_factors_baseline=["Month_1", "UniqueCarrier_000_OTHERS"], fit_intercept=True,
+                        partition_num=3)
+    clean = df.dropna().reset_index(drop=True)
+    assert des.n_rows_read == n and des.y.numel() == clean.shape[0]
+    # the pandas route on the same data
+    ref = clean.copy()
+    ref["ArrDelay"] = (ref["ArrDelay"] > 0).astype(float)
+    ref.insert(0, "partition_id", np.arange(ref.shape[0]) % 3)
+    info = dummies.select_dummy_factors(dummies.dummy_factors_counts(ref, ["Month", "UniqueCarrier"]), [1, 0.8])
+    assert {k: sorted(map(str, v)) for k, v in des.dummy_info["factor_selected"].items()} == \
+           {k: sorted(map(str, v)) for k, v in info["factor_selected"].items()}
+    assert sorted(des.dummy_info["factor_selected_names"]["UniqueCarrier"]) == sorted(info["factor_selected_names"]["UniqueCarrier"])
+    desc = ref[["DepTime", "Distance", "Year"]].describe()
+    for c in ["DepTime", "Distance", "Year"]:
+        assert np.allclose(des.data_info[c][:3], desc[c].to_numpy()[:3], rtol=1e-12)
+    data_info = {c: desc[c].to_numpy() for c in ["DepTime", "Distance", "Year"]}
+    want = models.logistic_model_partitions(ref, "ArrDelay", fit_intercept=True, dummy_info=info,
+                                            dummy_factors_baseline=["Month_1", "UniqueCarrier_000_OTHERS"],
+                                            data_info=data_info)
+    got = ingest.fit(des, fit_intercept=True)
+    assert list(got.columns) == list(want.columns) and got.shape == want.shape
+    assert np.max(np.abs(got["coef"].to_numpy() - want["coef"].to_numpy())) < 1e-8
+    assert relfro(got.iloc[:, 3:].to_numpy(), want.iloc[:, 3:].to_numpy()) < 1e-9
+
+
+def test_spark_adapter_udf_and_schema_on_a_fake_grouped_frame():
+    """f-4: the applyInPandas adapter — schema in convert_schema's order, int par_id, one call per partition group —
+    driven by a stand-in for ``data_sdf.groupby("partition_id").applyInPandas`` (Spark itself is absent here)."""
+    from dlsa_b200 import spark_adapter
+    from dlsa.dlsa import dlsa_mapred
+    df, K, g = games_frame()
+    usecols_x = [f"G{i}" for i in range(1, 11)]
+    udf, schema = spark_adapter.make_logistic_model_udf(usecols_x, "label")
+    assert schema.startswith("`par_id` int, `coef` double, `Sig_invMcoef` double, `G1` double")
+
+    class FakeGrouped:
+        def __init__(self, pdf, key):
+            self.pdf, self.key = pdf, key
+
+        def applyInPandas(self, fn, schema):
+            names = [f.split("`")[1] for f in schema.split(", ")]
+            outs = [fn(part.reset_index(drop=True)) for _, part in self.pdf.groupby(self.key)]
+            assert all(list(o.columns) == names for o in outs)
+            return pd.concat(outs, ignore_index=True)
+
+    class FakeSdf:
+        def __init__(self, pdf):
+            self.pdf = pdf
+
+        def groupby(self, key):
+            return FakeGrouped(self.pdf, key)
+
+    mapped = spark_adapter.map_on_executors(FakeSdf(df), usecols_x, "label")
+    assert mapped["par_id"].dtype == np.int32 and mapped.shape == (K * 10, 13)
+    mr = dlsa_mapred(mapped)
+    assert np.max(np.abs(mr["beta_byOLS"].to_numpy() - g["ref_beta_byOLS"])) < 1e-8
+    batched = spark_adapter.map_on_driver(df, "label")
+    assert np.max(np.abs(batched["coef"].to_numpy() - mapped["coef"].to_numpy())) < 1e-10
