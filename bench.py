@@ -426,7 +426,8 @@ class AirlineDense(Workload):
         row0 = ctx.rank * self.n
         n_levels = [L - 1 for L in synth.AIRLINE_LEVELS]
         px = synth.AIRLINE_NUM + sum(n_levels)
-        self.X = torch.zeros(self.n, px, dtype=torch.float64, device=ctx.dev)
+        # odd width: an even row pitch keeps every row 16-byte aligned (TMA row copies instead of 8-byte cp.async)
+        self.X = torch.zeros(self.n, px + (px & 1), dtype=torch.float64, device=ctx.dev)[:, :px]
         self.y = torch.empty(self.n, dtype=torch.float64, device=ctx.dev)
         base = torch.as_tensor(np.concatenate([[0], np.cumsum(n_levels)[:-1]]).astype(np.int32) + synth.AIRLINE_NUM,
                                device=ctx.dev)
