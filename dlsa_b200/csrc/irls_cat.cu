@@ -13,6 +13,13 @@
 //                                                          per lane, the second row's sum forwarded in registers when both
 //                                                          hit the same level — no atomics, fixed summation order; codes
 //                                                          of baseline levels point at a sink row (no predicates)
+//                                                          Categoricals with at most 16 levels (up to 6 tiles of 8 levels
+//                                                          in total) skip the scatter: their H[level, z] block is
+//                                                          one-hot(level)' (w z') on DMMA, 8 levels per tile, the one-hot
+//                                                          operand built from the row's table offset by one compare —
+//                                                          the FP64 pipe is idle here and the shared-memory pipe is the
+//                                                          bound (r02: 26 wavefronts per row before, profiles/).  Only
+//                                                          their g column stays in the scatter.
 //   H[level, level]   = H[level, 1]  (the intercept column of the block above)
 //   H[level, level']  = sum w over rows holding both       (different categorical columns) — a weighted 2-D histogram:
 //                                                          64-bit fixed-point RED.ADD into an L2-resident table
@@ -34,6 +41,7 @@ constexpr int kCatMaxNum = 7;    // numeric columns (z = [1 | numerics] fills on
 constexpr int kCatMaxWarps = 12;
 constexpr int kCatStages = 2;
 constexpr int kCatMaxRowsPerCta = 1 << 20;
+constexpr int kCatMaxTiles = 6;     // 8-level DMMA tiles for the narrow categoricals
 constexpr int kCatMaxLevels = 248;  // one byte per level index, 0xFF = no level
 constexpr int kTabPitch = 9;        // doubles per level: w*z (8) | r
 constexpr double kWScale = 17592186044416.0;  // 2^44
@@ -63,9 +71,16 @@ struct CatArgs {
     int Ltot, Lpad, npairs;
     int cat_lo[kCatMaxC + 1];            // level-space offsets of each categorical column
     int pair_off[kCatMaxC * kCatMaxC];   // offset of the (c, c') block, c < c', in the pair table
+    int pair_ld[kCatMaxC];               // levels of the column + 1: cell (0, .) and (., 0) of a block are sinks
     double* part_d;                      // [K*S, stride_d]: Dz 64 | gz 8 | ll 1 | pad to 80 | table [Lpad][9]
     unsigned long long* part_i;          // [K*S, stride_i]: pairs [npairs]
     int64_t stride_d, stride_i;
+    int nslots;                          // scatter slots in use (<= 96)
+    unsigned char slot[96];              // slot -> categorical * 16 + column (0..7 = w z', 8 = r)
+    int ntiles;                          // DMMA level tiles in use
+    int tile_cat[kCatMaxTiles];          // categorical column of the tile
+    int tile_lev0[kCatMaxTiles];         // first level (level-space index) of the tile
+    int tile_nlev[kCatMaxTiles];         // levels of the tile that exist (1..8)
 };
 
 __device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, bool pred) {
@@ -76,6 +91,12 @@ __device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void* src, b
     const int sz = pred ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -85,9 +106,21 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, long long v) 
     asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+template <int N, int NC>
+__device__ __forceinline__ void pair_reds(const CatArgs& a, unsigned long long* pairs, const int (&li)[NC], long long wfix) {
+    if constexpr (N <= NC) {
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+#pragma unroll
+            for (int d = c + 1; d < N; ++d)
+                red_add_u64(pairs + (unsigned)(a.pair_off[c * kCatMaxC + d] + li[c] * a.pair_ld[d] + li[d]), wfix);
+        }
+    }
+}
+
 // ROUNDS = ceil(9 * n_cat / 32): scatter slots (categorical c, column j in 0..8) are dealt to the 32 lanes round by round.
-// NC = categorical columns compiled into the row stage (4 or 8).
-template <int ROUNDS, int NC>
+// NC = categorical columns compiled into the row stage (4 or 8).  NTILE = compiled DMMA level tiles (0, 2, 4, 6).
+template <int ROUNDS, int NC, int NTILE>
 __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const CatArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = blockIdx.x / a.S;
@@ -141,6 +174,19 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
             const int nv = (int)((r1 - R0 < 32) ? (r1 - R0) : 32);
             unsigned char* st = ring + (size_t)(gi % kCatStages) * kStageBytes;
             const uint32_t zs = smem_u32(st), cs = zs + kStageZ, ys = cs + kStageC;
+            if (nv == 32 && a.ldn == n_num) {  // the common case: three contiguous runs, no predicates, one address each
+                const char* zsrc = reinterpret_cast<const char*>(a.num + R0 * n_num) + 8 * lane;
+                const char* csrc = reinterpret_cast<const char*>(a.codes + R0 * n_cat) + 4 * lane;
+#pragma unroll
+                for (int i = 0; i < kCatMaxNum; ++i)
+                    if (i < n_num) cp_async8(zs + 8 * lane + 256 * i, zsrc + 256 * i);
+#pragma unroll
+                for (int i = 0; i < kCatMaxC; ++i)
+                    if (i < n_cat) cp_async4(cs + 4 * lane + 128 * i, csrc + 128 * i);
+                cp_async8(ys + 8 * lane, a.y + R0 + lane);
+                cp_async_commit();
+                return;
+            }
             if (a.ldn == n_num) {
                 const double* src = a.num + R0 * n_num;
                 for (int i = 0; i < n_num; ++i) {
@@ -178,11 +224,22 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
     for (int q = 0; q < ROUNDS; ++q) {
         const int sidx = 32 * q + lane;
         int c = 8, j = 9;       // idle
-        if (sidx < 8 * n_cat) { c = sidx >> 3; j = sidx & 7; }
-        else if (sidx < 9 * n_cat) { c = sidx - 8 * n_cat; j = 8; }
+        if (sidx < a.nslots) { c = a.slot[sidx] >> 4; j = a.slot[sidx] & 15; }
         slot_to[q] = toff_u32 + 4 * c;
         slot_wz[q] = wz_u32 + 8 * j;
         slot_tb[q] = tab_u32 + 8 * (j == 9 ? 0 : j);
+    }
+    // DMMA level tiles: lane (m = lane >> 2, k = lane & 3) holds one-hot[level lev0 + m][row 4 ks + k] of the A operand
+    int tile_cmp[NTILE > 0 ? NTILE : 1];
+    uint32_t tile_to[NTILE > 0 ? NTILE : 1];
+    double td0[NTILE > 0 ? NTILE : 1], td1[NTILE > 0 ? NTILE : 1];
+#pragma unroll
+    for (int t = 0; t < NTILE; ++t) {
+        const bool on = t < a.ntiles;
+        tile_cmp[t] = on ? (a.tile_lev0[t] + (lane >> 2)) * (kTabPitch * 8) : -1;   // offsets are >= 0: -1 never matches
+        tile_to[t] = toff_u32 + 4 * (on ? a.tile_cat[t] : 8) + 2 * (lane & 3) * (kToPitch * 4);
+        td0[t] = 0.0;
+        td1[t] = 0.0;
     }
 
     double dz0 = 0.0, dz1 = 0.0, ll = 0.0;
@@ -260,32 +317,42 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
             trow[1] = make_int4(to[4], to[5], to[6], to[7]);
             trow[2] = make_int4(sink_off, sink_off, sink_off, sink_off);
         }
-        {   // weighted pair histogram: straight-line code, a pair with a baseline level (or an invalid row) adds into
-            // this lane's sink cell behind the table instead of branching around the RED
+        {   // weighted pair histogram: every (c, d) block carries a sink row and a sink column (index 0) that take the rows
+            // with a baseline level, so the cell index is two multiply-adds and the REDs are unconditional
             const long long wfix = __double2ll_rn(w * kWScale);
             int li[NC];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) li[c] = lev[c] - a.cat_lo[c < n_cat ? c : 0];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-#pragma unroll
-                for (int d = c + 1; d < NC; ++d) {
-                    if (d < n_cat) {  // warp-uniform
-                        const int idx = a.pair_off[c * kCatMaxC + d] + li[c] * (a.cat_lo[d + 1] - a.cat_lo[d]) + li[d];
-                        red_add_u64(pairs + ((lev[c] >= 0 && lev[d] >= 0) ? idx : a.npairs + lane), wfix);
-                    }
-                }
+            for (int c = 0; c < NC; ++c) li[c] = lev[c] < 0 ? 0 : lev[c] - a.cat_lo[c < n_cat ? c : 0] + 1;
+            switch (n_cat) {
+                case 2: pair_reds<2, NC>(a, pairs, li, wfix); break;
+                case 3: pair_reds<3, NC>(a, pairs, li, wfix); break;
+                case 4: pair_reds<4, NC>(a, pairs, li, wfix); break;
+                case 5: pair_reds<5, NC>(a, pairs, li, wfix); break;
+                case 6: pair_reds<6, NC>(a, pairs, li, wfix); break;
+                case 7: pair_reds<7, NC>(a, pairs, li, wfix); break;
+                case 8: pair_reds<8, NC>(a, pairs, li, wfix); break;
+                default: break;
             }
         }
         __syncwarp();
 
-        // ---- dense z block: 8 k-steps of 4 rows, one DMMA each: A = z, B = w z (already in shared memory) ----------
+        // ---- dense z block: 8 k-steps of 4 rows, one DMMA each: A = z, B = w z (already in shared memory); the narrow
+        // categoricals' H[level, z] tiles reuse B with A = one-hot(level) ---------------------------------------------
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-            const int src = 4 * ks + (lane & 3);
+            // the 4 rows of a k-step are 2 apart: with the 10-double row pitch of (w z', r) a half-warp's 16 operands then
+            // fall into 16 different bank pairs (consecutive rows collide: r02 ncu, 4 wavefronts per load instead of 2)
+            const int src = 8 * (ks >> 1) + (ks & 1) + 2 * (lane & 3);
             double zz = 1.0;
             if (jcol > 0) zz = (jcol - 1 < n_num) ? zs[src * n_num + jcol - 1] : 0.0;
-            dmma884(dz0, dz1, zz, wz[src * kWzPitch + jcol]);
+            const double bw = wz[src * kWzPitch + jcol];
+            dmma884(dz0, dz1, zz, bw);
+#pragma unroll
+            for (int t = 0; t < NTILE; ++t) {
+                int o;
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(tile_to[t] + (uint32_t)(8 * (ks >> 1) + (ks & 1)) * (kToPitch * 4u)));
+                dmma884(td0[t], td1[t], (o == tile_cmp[t]) ? 1.0 : 0.0, bw);
+            }
         }
 
         // ---- level blocks: scatter-add into the warp's table, two rows per step ------------------------------------
@@ -308,7 +375,7 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
             }
         };
         load_pair(0);
-#pragma unroll 2
+#pragma unroll
         for (int rp = 0; rp < 16; ++rp) {
             uint32_t ca[ROUNDS], cb[ROUNDS];
             double ta[ROUNDS], tb[ROUNDS], xa[ROUNDS], xb[ROUNDS];
@@ -330,6 +397,15 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
         __syncwarp();  // the stage and the row scratch are re-filled by the next iteration
     }
     cp_async_wait<0>();
+    // the DMMA tiles' sums go where the scatter would have put them (those cells were never touched)
+#pragma unroll
+    for (int t = 0; t < NTILE; ++t) {
+        if (t < a.ntiles && (lane >> 2) < a.tile_nlev[t]) {
+            double* cell = tab + (a.tile_lev0[t] + (lane >> 2)) * kTabPitch + 2 * (lane & 3);
+            cell[0] = td0[t];
+            cell[1] = td1[t];
+        }
+    }
 
     // ---- CTA reduction in a fixed warp order, straight into the workspace partial ----------------------------------
 #pragma unroll
@@ -408,8 +484,8 @@ __global__ void irls_cat_finalize_kernel(const CatArgs a, double* __restrict__ g
             } else {
                 const int c1 = cat_of(l1), c2 = cat_of(l2);
                 if (c1 != c2) {
-                    const int idx = a.pair_off[c1 * kCatMaxC + c2] + (l1 - a.cat_lo[c1]) * (a.cat_lo[c2 + 1] - a.cat_lo[c2]) +
-                                    (l2 - a.cat_lo[c2]);
+                    const int idx = a.pair_off[c1 * kCatMaxC + c2] + (l1 - a.cat_lo[c1] + 1) * a.pair_ld[c2] +
+                                    (l2 - a.cat_lo[c2] + 1);
                     for (int sl = 0; sl < a.S; ++sl)  // per-slice conversion: a slice sum is < 2^63, the partition sum may not be
                         v += (double)(long long)pi[sl * a.stride_i + idx] * (1.0 / kWScale);
                 }
@@ -456,7 +532,7 @@ void cat_plan(int K, int n_cat, const int* n_levels, int64_t max_part_rows, CatP
     pl.Ltot = 0;
     pl.npairs = 0;
     for (int c = 0; c < n_cat; ++c) {
-        pl.npairs += pl.Ltot * n_levels[c];  // every earlier level x this column's levels
+        for (int d = 0; d < c; ++d) pl.npairs += (n_levels[d] + 1) * (n_levels[c] + 1);  // + sink row and column
         pl.Ltot += n_levels[c];
     }
     pl.Lpad = (pl.Ltot + 7) / 8 * 8;
@@ -480,7 +556,7 @@ void cat_plan(int K, int n_cat, const int* n_levels, int64_t max_part_rows, CatP
     if (S < 1) S = 1;
     pl.S = (int)S;
     pl.stride_d = 80 + (int64_t)pl.Lpad * kTabPitch;
-    pl.stride_i = pl.npairs + 32;  // + one sink cell per lane for pairs that involve a baseline level
+    pl.stride_i = pl.npairs;
     pl.bytes_d = (size_t)K * S * pl.stride_d * 8;
     pl.bytes_i = (size_t)K * S * pl.stride_i * 8;
     // as many warps as shared memory allows (each owns a ring, a row scratch and a level table)
@@ -502,9 +578,9 @@ size_t irls_cat_workspace_bytes(int K, int n_cat, const int* n_levels, int64_t m
     return pl.bytes_d + pl.bytes_i + 256;
 }
 
-template <int ROUNDS, int NC>
+template <int ROUNDS, int NC, int NTILE>
 static int cat_launch_t(const CatArgs& a, const CatPlan& pl, cudaStream_t st) {
-    auto kern = irls_cat_kernel<ROUNDS, NC>;
+    auto kern = irls_cat_kernel<ROUNDS, NC, NTILE>;
     DLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     kern<<<a.K * a.S, pl.warps * 32, pl.smem, st>>>(a);
     count_launch();
@@ -546,8 +622,9 @@ int irls_cat_launch(const double* numeric, int64_t ldn, int n_num, const double*
         a.cat_lo[c] = lo;
         for (int d = 0; d < c; ++d) {
             a.pair_off[d * kCatMaxC + c] = off;
-            off += n_levels[d] * n_levels[c];
+            off += (n_levels[d] + 1) * (n_levels[c] + 1);
         }
+        a.pair_ld[c] = n_levels[c] + 1;
         lo += n_levels[c];
     }
     for (int c = n_cat; c <= kCatMaxC; ++c) a.cat_lo[c] = lo;
@@ -557,12 +634,73 @@ int irls_cat_launch(const double* numeric, int64_t ldn, int n_num, const double*
     a.stride_d = pl.stride_d;
     a.stride_i = pl.stride_i;
     DLSA_CUDA(cudaMemsetAsync(a.part_i, 0, pl.bytes_i, st));
-    const int rounds = (9 * n_cat + 31) / 32;  // 1..3
+    // narrow categoricals (<= 16 levels, narrowest first, <= kCatMaxTiles tiles in total) go to DMMA tiles; the others —
+    // and every g column — to the scatter slots
+    static const int tile_budget = [] {
+        const char* e = getenv("DLSA_CAT_DMMA_TILES");
+        int v = e ? atoi(e) : kCatMaxTiles;
+        return v < 0 ? 0 : (v > kCatMaxTiles ? kCatMaxTiles : v);
+    }();
+    bool on_dmma[kCatMaxC] = {};
+    for (;;) {
+        int best = -1;
+        for (int c = 0; c < n_cat; ++c)
+            if (!on_dmma[c] && n_levels[c] >= 1 && n_levels[c] <= 16 && (best < 0 || n_levels[c] < n_levels[best])) best = c;
+        if (best < 0 || a.ntiles + (n_levels[best] + 7) / 8 > tile_budget) break;
+        on_dmma[best] = true;
+        for (int b = 0; b < n_levels[best]; b += 8) {
+            a.tile_cat[a.ntiles] = best;
+            a.tile_lev0[a.ntiles] = a.cat_lo[best] + b;
+            a.tile_nlev[a.ntiles] = n_levels[best] - b < 8 ? n_levels[best] - b : 8;
+            ++a.ntiles;
+        }
+    }
+    // Slot layout: 64-bit shared accesses are served one HALF-warp at a time, so a scattered categorical's 2 + n_num
+    // columns (one run of consecutive doubles in its level's row) are kept inside one half-warp and the single g
+    // columns of the DMMA categoricals fill the gaps — two runs in one half-warp always overlap in some bank.
+    {
+        const int run = n_num + 2;                   // w | w z_1..n_num | r
+        int fill[6] = {0, 0, 0, 0, 0, 0};            // lanes used per half-warp (3 rounds x 2)
+        unsigned char lay[96];
+        for (int i = 0; i < 96; ++i) lay[i] = 0x89;  // idle: categorical 8 (always the sink row), column 9 (always 0.0)
+        auto place = [&](int c, int j0, int cnt, bool r_col) -> bool {
+            for (int h = 0; h < 6; ++h) {
+                if (fill[h] + cnt + (r_col ? 1 : 0) > 16) continue;
+                for (int j = 0; j < cnt; ++j) lay[16 * h + fill[h]++] = (unsigned char)(c * 16 + j0 + j);
+                if (r_col) lay[16 * h + fill[h]++] = (unsigned char)(c * 16 + 8);
+                return true;
+            }
+            return false;
+        };
+        bool ok = true;
+        for (int c = 0; c < n_cat && ok; ++c)
+            if (!on_dmma[c]) ok = place(c, 0, run - 1, true);
+        for (int c = 0; c < n_cat && ok; ++c)
+            if (on_dmma[c]) ok = place(c, 8, 1, false);
+        if (ok) {
+            int last = 0;
+            for (int h = 0; h < 6; ++h)
+                if (fill[h] > 0) last = 16 * h + 16;
+            a.nslots = last;
+            for (int i = 0; i < last; ++i) a.slot[i] = lay[i];
+        } else {  // more runs than half-warps (7+ scattered categoricals): dense packing, 9 n_cat <= 72 slots always fit
+            a.nslots = 0;
+            for (int c = 0; c < n_cat; ++c)
+                if (!on_dmma[c])
+                    for (int j = 0; j <= n_num; ++j) a.slot[a.nslots++] = (unsigned char)(c * 16 + j);
+            for (int c = 0; c < n_cat; ++c) a.slot[a.nslots++] = (unsigned char)(c * 16 + 8);
+        }
+    }
+    const int rounds = (a.nslots + 31) / 32;  // 1..3
+    const int ntile = (a.ntiles + 1) & ~1;
     const bool c4 = n_cat <= 4;
-    int rc;
-    if (rounds == 1) rc = cat_launch_t<1, 4>(a, pl, st);
-    else if (rounds == 2) rc = c4 ? cat_launch_t<2, 4>(a, pl, st) : cat_launch_t<2, 8>(a, pl, st);
-    else rc = cat_launch_t<3, 8>(a, pl, st);
+    int rc = DLSA_E_UNSUPPORTED;
+#define DLSA_CAT_CASE(R, T)                                                                     \
+    if (rounds == R && ntile == T) rc = c4 ? cat_launch_t<R, 4, T>(a, pl, st) : cat_launch_t<R, 8, T>(a, pl, st);
+    DLSA_CAT_CASE(1, 0) DLSA_CAT_CASE(1, 2) DLSA_CAT_CASE(1, 4) DLSA_CAT_CASE(1, 6)
+    DLSA_CAT_CASE(2, 0) DLSA_CAT_CASE(2, 2) DLSA_CAT_CASE(2, 4) DLSA_CAT_CASE(2, 6)
+    DLSA_CAT_CASE(3, 0) DLSA_CAT_CASE(3, 2) DLSA_CAT_CASE(3, 4) DLSA_CAT_CASE(3, 6)
+#undef DLSA_CAT_CASE
     if (rc != 0) return rc;
     irls_cat_finalize_kernel<<<K, 256, 0, st>>>(a, g, H, loglik);
     count_launch();

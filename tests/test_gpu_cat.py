@@ -51,6 +51,10 @@ CASES = [
     (3, [8, 8, 8, 8, 8, 8, 8, 8], True, True),  # 8 categorical columns, tiles aligned with the blocks
     (5, [1, 1, 30, 100], False, False),       # 132 levels -> 17 tiles
     (6, [40, 60, 90], True, False),           # 190 levels -> 24 tiles
+    (7, [20] * 8, True, True),                # 8 scattered categoricals: more 9-column runs than half-warps (dense packing)
+    (7, [5, 24, 24, 24, 24, 24, 24, 24], False, False),   # one DMMA tile + 7 scattered
+    (4, [16, 9, 16, 16], True, False),        # 6 DMMA tiles used up by the three 16-level columns; the 9-level one scatters
+    (1, [1, 8, 2, 17], True, True),           # tiles with 1, 8 and 2 live levels
 ]
 
 
