@@ -4,32 +4,34 @@
 // Replaces, for the dummy branch of logistic_model (dlsa/models.py:56-91: pd.get_dummies -> dense 0/1 columns ->
 // sklearn fit -> Sig_inv = X' diag(p(1-p)) X, :130), the same quantities as dlsa_irls_pass_f64 on the expanded X:
 //   g = X'(y - prob),  H = X' diag(prob(1-prob)) X,  loglik.
-// A row of the expanded X is z = [1 | x_1..x_q] (q <= 7 numerics) plus ONE 1 per categorical column, so
-//   H[z, z]           = sum w z z'                         one DMMA per 4 rows (8x8 tile)
-//   H[level, z]       = sum_{rows at that level} w z'      scatter-add into a WARP-PRIVATE shared-memory table
-//   g[level]          = sum_{rows at that level} r          [level][9]: lane = (categorical, column); the row stage leaves
-//                                                          (w z', r) and the table offset of every (row, categorical) in
-//                                                          shared memory, so a row pair costs 4 loads + 2 adds + 2 stores
-//                                                          per lane, the second row's sum forwarded in registers when both
-//                                                          hit the same level — no atomics, fixed summation order; codes
-//                                                          of baseline levels point at a sink row (no predicates)
-//                                                          Categoricals with at most 16 levels (up to 6 tiles of 8 levels
-//                                                          in total) skip the scatter: their H[level, z] block is
-//                                                          one-hot(level)' (w z') on DMMA, 8 levels per tile, the one-hot
-//                                                          operand built from the row's table offset by one compare —
-//                                                          the FP64 pipe is idle here and the shared-memory pipe is the
-//                                                          bound (r02: 26 wavefronts per row before, profiles/).  Only
-//                                                          their g column stays in the scatter.
-//   H[level, level]   = H[level, 1]  (the intercept column of the block above)
-//   H[level, level']  = sum w over rows holding both       (different categorical columns) — a weighted 2-D histogram:
-//                                                          64-bit fixed-point RED.ADD into an L2-resident table
+// A row of the expanded X is z = [1 | x_1..x_q] (q <= 7 numerics) plus ONE 1 per categorical column.  The row stage
+// (lane = row) leaves b = (r, w z_1, .., w z_7) per row in shared memory; then
+//   H[z, z], g[z]      = sum z (x) b                        one DMMA per 4 rows: column 0 of the product is g[z], row 0 gives
+//                                                           the intercept row by symmetry, sum w is a scalar accumulator
+//   H[level, z_j],     = sum_{rows at that level} b          NARROW categoricals (<= 16 levels, <= 6 tiles of 8 levels in
+//   g[level]                                                 total): one-hot(level)' b on DMMA — the FP64 pipe is idle here.
+//                                                           WIDE categoricals: scatter-add into a WARP-PRIVATE shared-memory
+//                                                           table, two categoricals per table, level l of the first in
+//                                                           bytes 0..63 of row l and of the second in bytes 64..127: a
+//                                                           half-warp (2 categoricals x 8 columns) then touches 16 different
+//                                                           bank pairs whatever the levels are, and the two half-warps work
+//                                                           on two consecutive rows at once (rows that share a level are
+//                                                           applied one after the other) — no atomics, fixed summation order;
+//                                                           baseline levels point at a sink row
+//   H[level, level']   = sum w over rows holding both        (different categorical columns) — a weighted 2-D histogram:
+//                                                           64-bit fixed-point RED.ADD into an L2-resident table whose
+//                                                           (c, d) block has a sink row and a sink column for baselines
+//   H[level, level]    = H[level, 1] = sum_j block(c, d)[level][j]   every row holds exactly one level (or the baseline) of the
+//                                                           partner column d, so the row sums of a pair block — sinks
+//                                                           included — are the level's own weight: no ninth scatter column
 // Algorithmic traffic per row: 8 q + 4 c + 8 bytes (airline shape: 84 B instead of 1456 B).  Fixed-point sums are
 // exact integer additions => the histogram part is bitwise independent of the order in which rows arrive; resolution
 // 2^-44 (w <= 1/4) against sums of at most 2^20 rows per CTA.
 //
-// v1 of this kernel did H[level, z] on DMMA with a one-hot operand and per-tile skipping (profiles/r01_k1c_*_v1.*):
-// ptxas predicates the skipped DMMAs and a predicated-off DMMA still holds the FP64 pipe for 16 cycles, so all 25
-// tile slots per 4 rows were paid (3.07 ms for 15M rows); an indirect-branch dispatch was slower still (5.0 ms).
+// History (profiles/): v1 did every H[level, z] tile on DMMA with per-tile skipping — a predicated-off DMMA still holds
+// the FP64 pipe for 16 cycles (r01).  v2 scattered nine columns of every categorical with lane = (categorical, column):
+// 26 shared-memory wavefronts per row, LSU data pipe 70-80 % busy (r02_cat_c3_ncu_summary.csv).  This version: 8 columns,
+// conflict-free by construction, two rows per instruction.
 #include "common.cuh"
 
 namespace dlsa {
@@ -38,21 +40,13 @@ namespace {
 
 constexpr int kCatMaxC = 8;      // categorical columns
 constexpr int kCatMaxNum = 7;    // numeric columns (z = [1 | numerics] fills one 8-wide tile)
-constexpr int kCatMaxWarps = 12;
+constexpr int kCatMaxWarps = 16;
 constexpr int kCatStages = 2;
 constexpr int kCatMaxRowsPerCta = 1 << 20;
 constexpr int kCatMaxTiles = 6;     // 8-level DMMA tiles for the narrow categoricals
-constexpr int kCatMaxLevels = 248;  // one byte per level index, 0xFF = no level
-constexpr int kTabPitch = 9;        // doubles per level: w*z (8) | r
+constexpr int kTabPitch = 9;        // doubles per level in the PARTIALS: [unused | w z_1..7 | r]
 constexpr double kWScale = 17592186044416.0;  // 2^44
-// per-warp, per-stage shared memory: 32 rows of numerics (7 doubles), codes (8 ints), labels
-constexpr int kStageZ = 32 * kCatMaxNum * 8;
-constexpr int kStageC = 32 * kCatMaxC * 4;
-constexpr int kStageY = 32 * 8;
-constexpr int kStageBytes = kStageZ + kStageC + kStageY;  // 3072
-constexpr int kWzPitch = 10;                               // doubles per row: w | w*z_1..7 | r | 0
-constexpr int kToPitch = 12;                                // ints per row: offsets of categoricals 0..7 | 4 x sink (idle lanes)
-constexpr int kRowScratch = 32 * kWzPitch * 8 + 32 * kToPitch * 4;  // (w z', r) per row | table byte offset per (row, categorical)
+constexpr int kBPitch = 10;                                // doubles per row of b: r | w z_1..7 | 2 pad (bank spread, see the DMMA stage)
 
 struct CatArgs {
     const double* num;
@@ -60,6 +54,7 @@ struct CatArgs {
     int n_num;
     const int* codes;
     int n_cat;
+    int n_pair_cats;                     // max(n_cat, 2): a lone categorical gets an empty partner for its weight sums
     const double* mean;
     const double* sd;
     const double* y;
@@ -72,15 +67,23 @@ struct CatArgs {
     int cat_lo[kCatMaxC + 1];            // level-space offsets of each categorical column
     int pair_off[kCatMaxC * kCatMaxC];   // offset of the (c, c') block, c < c', in the pair table
     int pair_ld[kCatMaxC];               // levels of the column + 1: cell (0, .) and (., 0) of a block are sinks
+    int partner[kCatMaxC];               // the column whose pair block yields this column's level weights
     double* part_d;                      // [K*S, stride_d]: Dz 64 | gz 8 | ll 1 | pad to 80 | table [Lpad][9]
     unsigned long long* part_i;          // [K*S, stride_i]: pairs [npairs]
     int64_t stride_d, stride_i;
-    int nslots;                          // scatter slots in use (<= 96)
-    unsigned char slot[96];              // slot -> categorical * 16 + column (0..7 = w z', 8 = r)
+    int n_wide;                          // scattered categoricals; wide slot v = 2 * round + half
+    int cat_wide[kCatMaxC];              // categorical -> wide slot, or -1 (narrow)
+    int cat_row[kCatMaxC];               // categorical -> row of the per-row int scratch (wide slots first, then narrow)
+    int cat_tab[kCatMaxC];               // wide: byte offset of level 0 of this categorical inside the warp's tables
+    int cat_sink[kCatMaxC];              // wide: byte offset of its half of the round's sink row
+    int tab_bytes;                       // per-warp tables, all rounds
+    int share_tables;                    // 1: warps 2 i and 2 i + 1 take turns on one set of tables; 0: one set per warp
+    int stage_bytes, front_bytes;        // one ring stage (numerics | codes | labels); ring + row scratch (tables follow)
     int ntiles;                          // DMMA level tiles in use
-    int tile_cat[kCatMaxTiles];          // categorical column of the tile
-    int tile_lev0[kCatMaxTiles];         // first level (level-space index) of the tile
+    int tile_row[kCatMaxTiles];          // row of the per-row int scratch holding the categorical's codes
+    int tile_code0[kCatMaxTiles];        // first code (level within the categorical) of the tile
     int tile_nlev[kCatMaxTiles];         // levels of the tile that exist (1..8)
+    int tile_lev0[kCatMaxTiles];         // level-space index of the tile's first level
 };
 
 __device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, bool pred) {
@@ -106,6 +109,10 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, long long v) 
     asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 template <int N, int NC>
 __device__ __forceinline__ void pair_reds(const CatArgs& a, unsigned long long* pairs, const int (&li)[NC], long long wfix) {
     if constexpr (N <= NC) {
@@ -118,8 +125,8 @@ __device__ __forceinline__ void pair_reds(const CatArgs& a, unsigned long long* 
     }
 }
 
-// ROUNDS = ceil(9 * n_cat / 32): scatter slots (categorical c, column j in 0..8) are dealt to the 32 lanes round by round.
-// NC = categorical columns compiled into the row stage (4 or 8).  NTILE = compiled DMMA level tiles (0, 2, 4, 6).
+// ROUNDS = ceil(wide categoricals / 2) (0..4).  NC = categorical columns compiled into the row stage (4 or 8).
+// NTILE = compiled DMMA level tiles (0, 2, 4, 6).
 template <int ROUNDS, int NC, int NTILE>
 __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const CatArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -129,20 +136,25 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_num = a.n_num, n_cat = a.n_cat;
-    const int tab_doubles = a.Lpad * kTabPitch;          // what the CTA reduction reads; the sink row follows it
-    const int tab_alloc = ((a.Lpad + 1) * kTabPitch + 1) & ~1;   // even: every warp's block stays 16-byte aligned
 
-    // shared: per warp [ring | row scratch | table + sink row] ; then beta (8 + Lpad)
-    const size_t per_warp = (size_t)kCatStages * kStageBytes + kRowScratch + (size_t)tab_alloc * 8;
-    unsigned char* mine = smem_raw + (size_t)warp * per_warp;
+    // shared: per warp [ring | b rows | int rows]; the level tables, one set per warp or — when that buys at least four more
+    // warps per SM (shared memory is what limits them, and a table is in use for a fifth of a warp's time) — one set per
+    // warp PAIR, warps 2 i and 2 i + 1 taking turns (see the scatter stage); then beta (8 + Lpad), two mbarriers per pair
+    const int stage_z = 256 * n_num, stage_c = 128 * n_cat;   // 32 rows of numerics, of codes (then 32 labels)
+    const int tshift = a.share_tables ? 1 : 0;
+    const int npair = (nwarps + tshift) >> tshift;   // sets of tables
+    unsigned char* mine = smem_raw + (size_t)warp * a.front_bytes;
     unsigned char* ring = mine;
-    double* wz = reinterpret_cast<double*>(mine + kCatStages * kStageBytes);                              // [32][10]
-    int* toff = reinterpret_cast<int*>(mine + kCatStages * kStageBytes + 32 * kWzPitch * 8);              // [32][12]
-    double* tab = reinterpret_cast<double*>(mine + kCatStages * kStageBytes + kRowScratch);
-    double* bz = reinterpret_cast<double*>(smem_raw + (size_t)nwarps * per_warp);
+    double* bs = reinterpret_cast<double*>(mine + kCatStages * a.stage_bytes);                          // [32][10]
+    int* irow = reinterpret_cast<int*>(mine + kCatStages * a.stage_bytes + 32 * kBPitch * 8);           // [n_cat][32]
+    unsigned char* tab_all = smem_raw + (size_t)nwarps * a.front_bytes;
+    unsigned char* tab = tab_all + (size_t)(warp >> tshift) * a.tab_bytes;
+    double* bz = reinterpret_cast<double*>(tab_all + (size_t)npair * a.tab_bytes);
     double* bl = bz + 8;
+    const uint32_t turn = smem_u32(bl + a.Lpad) + 16u * (warp >> 1);   // [0]: the even warp is done, [1]: the odd warp is done
+    const bool paired = a.share_tables && (warp | 1) < nwarps;         // the last warp of an odd count has its tables alone
 
-    // coefficients in internal order: [intercept | numerics (7) | levels]; zero this warp's table
+    // coefficients in internal order: [intercept | numerics (7) | levels]; zero this warp's tables
     {
         const int p = a.fit_intercept + n_num + a.Ltot;
         const double* bk = a.beta + (size_t)k * p;
@@ -153,7 +165,12 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
             else if (i - 8 < a.Ltot) v = bk[a.fit_intercept + n_num + (i - 8)];
             bz[i] = v;
         }
-        for (int i = lane; i < tab_alloc; i += 32) tab[i] = 0.0;
+        double* t = reinterpret_cast<double*>(tab_all);
+        for (int i = threadIdx.x; i < npair * (a.tab_bytes / 8); i += blockDim.x) t[i] = 0.0;
+        if (lane == 0 && (warp & 1) == 0) {
+            mbar_init(turn, 1);
+            mbar_init(turn + 8, 1);
+        }
     }
     __syncthreads();
 
@@ -165,6 +182,7 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
     const int64_t r1 = (r0 + per < p1) ? r0 + per : p1;
     const int64_t ngroups = r1 > r0 ? (r1 - r0 + 31) / 32 : 0;
     const int64_t my_groups = ngroups > warp ? (ngroups - warp + nwarps - 1) / nwarps : 0;
+    const int64_t mate_groups = ngroups > (warp ^ 1) ? (ngroups - (warp ^ 1) + nwarps - 1) / nwarps : 0;   // even >= odd
 
     unsigned long long* pairs = a.part_i + (size_t)blockIdx.x * a.stride_i;
 
@@ -172,8 +190,8 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
         if (gi < my_groups) {
             const int64_t R0 = r0 + (warp + gi * nwarps) * 32;
             const int nv = (int)((r1 - R0 < 32) ? (r1 - R0) : 32);
-            unsigned char* st = ring + (size_t)(gi % kCatStages) * kStageBytes;
-            const uint32_t zs = smem_u32(st), cs = zs + kStageZ, ys = cs + kStageC;
+            unsigned char* st = ring + (size_t)(gi % kCatStages) * a.stage_bytes;
+            const uint32_t zs = smem_u32(st), cs = zs + stage_z, ys = cs + stage_c;
             if (nv == 32 && a.ldn == n_num) {  // the common case: three contiguous runs, no predicates, one address each
                 const char* zsrc = reinterpret_cast<const char*>(a.num + R0 * n_num) + 8 * lane;
                 const char* csrc = reinterpret_cast<const char*>(a.codes + R0 * n_cat) + 4 * lane;
@@ -213,39 +231,33 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
         cp_async_commit();  // one (possibly empty) group per call keeps the wait_group arithmetic uniform
     };
 
-    // per-lane scatter slots: round q handles slot 32 q + lane = (categorical c, column j); j = 8 is the g column.  Idle
-    // lanes take "categorical 8", whose offset is always the sink row, and column 9 of the (w z', r) row, which is 0.0.
-    const uint32_t wz_u32 = smem_u32(wz), toff_u32 = smem_u32(toff), tab_u32 = smem_u32(tab);
-    const int sink_off = a.Lpad * kTabPitch * 8;
-    uint32_t slot_to[ROUNDS];   // shared address of toff[0][c]
-    uint32_t slot_wz[ROUNDS];   // shared address of wz[0][j]
-    uint32_t slot_tb[ROUNDS];   // shared address of tab[0][j]
+    // scatter lanes: half-warp h works on row 2 rp + h; inside it lane = (which categorical of the round's two, column j);
+    // column 0 is r (-> g[level]), column j >= 1 is w z_j
+    const uint32_t bs_u32 = smem_u32(bs), irow_u32 = smem_u32(irow), tab_u32 = smem_u32(tab);
+    const int half = lane >> 4, colj = lane & 7;
+    uint32_t sc_to[ROUNDS > 0 ? ROUNDS : 1];   // shared address of this lane's categorical's offsets of rows 0, 1
+    bool sc_on[ROUNDS > 0 ? ROUNDS : 1];
 #pragma unroll
     for (int q = 0; q < ROUNDS; ++q) {
-        const int sidx = 32 * q + lane;
-        int c = 8, j = 9;       // idle
-        if (sidx < a.nslots) { c = a.slot[sidx] >> 4; j = a.slot[sidx] & 15; }
-        slot_to[q] = toff_u32 + 4 * c;
-        slot_wz[q] = wz_u32 + 8 * j;
-        slot_tb[q] = tab_u32 + 8 * (j == 9 ? 0 : j);
+        const int v = 2 * q + ((lane >> 3) & 1);
+        sc_on[q] = v < a.n_wide && colj <= n_num;
+        sc_to[q] = irow_u32 + (uint32_t)(v < a.n_wide ? v : 0) * 128u;
     }
-    // DMMA level tiles: lane (m = lane >> 2, k = lane & 3) holds one-hot[level lev0 + m][row 4 ks + k] of the A operand
+    const uint32_t sc_b = bs_u32 + (uint32_t)half * (kBPitch * 8u) + 8u * colj;   // b[row 0 + half][j]
+    // DMMA level tiles: lane (m = lane >> 2, k = lane & 3) holds one-hot[code code0 + m][row] of the A operand
     int tile_cmp[NTILE > 0 ? NTILE : 1];
     uint32_t tile_to[NTILE > 0 ? NTILE : 1];
     double td0[NTILE > 0 ? NTILE : 1], td1[NTILE > 0 ? NTILE : 1];
 #pragma unroll
     for (int t = 0; t < NTILE; ++t) {
         const bool on = t < a.ntiles;
-        tile_cmp[t] = on ? (a.tile_lev0[t] + (lane >> 2)) * (kTabPitch * 8) : -1;   // offsets are >= 0: -1 never matches
-        tile_to[t] = toff_u32 + 4 * (on ? a.tile_cat[t] : 8) + 2 * (lane & 3) * (kToPitch * 4);
+        tile_cmp[t] = on ? a.tile_code0[t] + (lane >> 2) : -2;   // codes are >= -1: -2 never matches
+        tile_to[t] = irow_u32 + (uint32_t)(on ? a.tile_row[t] : 0) * 128u + 8u * (lane & 3);
         td0[t] = 0.0;
         td1[t] = 0.0;
     }
 
-    double dz0 = 0.0, dz1 = 0.0, ll = 0.0;
-    double gz[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) gz[j] = 0.0;
+    double dz0 = 0.0, dz1 = 0.0, ll = 0.0, sw = 0.0;
 
     for (int64_t gi = 0; gi < kCatStages - 1; ++gi) issue(gi);
 
@@ -256,10 +268,10 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
         __syncwarp();
         const int64_t R0 = r0 + (warp + gi * nwarps) * 32;
         const int nv = (int)((r1 - R0 < 32) ? (r1 - R0) : 32);
-        unsigned char* st = ring + (size_t)(gi % kCatStages) * kStageBytes;
+        unsigned char* st = ring + (size_t)(gi % kCatStages) * a.stage_bytes;
         double* zs = reinterpret_cast<double*>(st);
-        const int* cs = reinterpret_cast<const int*>(st + kStageZ);
-        const double* ys = reinterpret_cast<const double*>(st + kStageZ + kStageC);
+        const int* cs = reinterpret_cast<const int*>(st + stage_z);
+        const double* ys = reinterpret_cast<const double*>(st + stage_z + stage_c);
 
         // ---- row stage: lane = row -----------------------------------------------------------------------
         const bool valid = lane < nv;
@@ -278,20 +290,19 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
                 eta = fma(v, bz[1 + j], eta);
             }
         }
-        int lev[NC];
-        int to[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) to[c] = sink_off;
+        int li[NC];   // 1 + level within the column; 0 = baseline level, no such column, or no such row
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            lev[c] = -1;
-            if (c < n_cat && valid) {
-                const int code = cs[lane * n_cat + c];
+            li[c] = 0;
+            if (c < n_cat) {
+                const int code = valid ? cs[lane * n_cat + c] : -1;
                 if (code >= 0) {
-                    lev[c] = a.cat_lo[c] + code;
-                    eta += bl[lev[c]];
-                    to[c] = lev[c] * (kTabPitch * 8);
+                    li[c] = code + 1;
+                    eta += bl[a.cat_lo[c] + code];
                 }
+                // wide: byte offset of the level's half row in the warp's tables; narrow: the code itself
+                const int wide_to = code >= 0 ? a.cat_tab[c] + code * 128 : a.cat_sink[c];
+                irow[a.cat_row[c] * 32 + lane] = a.cat_wide[c] >= 0 ? wide_to : code;
             }
         }
         double w = 0.0, r = 0.0;
@@ -302,28 +313,18 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
             r = yy - prob;
             if (a.want_ll) ll += yy * eta - log1pexp_f64(eta);
         }
-        gz[0] += r;
-#pragma unroll
-        for (int j = 0; j < kCatMaxNum; ++j) gz[1 + j] = fma(r, z[j], gz[1 + j]);
-        {   // (w, w z_1..7, r, 0) and the table offsets of this row
-            double2* wrow = reinterpret_cast<double2*>(wz + lane * kWzPitch);
-            wrow[0] = make_double2(w, w * z[0]);
-            wrow[1] = make_double2(w * z[1], w * z[2]);
-            wrow[2] = make_double2(w * z[3], w * z[4]);
-            wrow[3] = make_double2(w * z[5], w * z[6]);
-            wrow[4] = make_double2(r, 0.0);
-            int4* trow = reinterpret_cast<int4*>(toff + lane * kToPitch);
-            trow[0] = make_int4(to[0], to[1], to[2], to[3]);
-            trow[1] = make_int4(to[4], to[5], to[6], to[7]);
-            trow[2] = make_int4(sink_off, sink_off, sink_off, sink_off);
+        sw += w;
+        {   // b = (r, w z_1..7) of this row
+            double2* brow = reinterpret_cast<double2*>(bs + lane * kBPitch);
+            brow[0] = make_double2(r, w * z[0]);
+            brow[1] = make_double2(w * z[1], w * z[2]);
+            brow[2] = make_double2(w * z[3], w * z[4]);
+            brow[3] = make_double2(w * z[5], w * z[6]);
         }
         {   // weighted pair histogram: every (c, d) block carries a sink row and a sink column (index 0) that take the rows
             // with a baseline level, so the cell index is two multiply-adds and the REDs are unconditional
             const long long wfix = __double2ll_rn(w * kWScale);
-            int li[NC];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) li[c] = lev[c] < 0 ? 0 : lev[c] - a.cat_lo[c < n_cat ? c : 0] + 1;
-            switch (n_cat) {
+            switch (a.n_pair_cats) {
                 case 2: pair_reds<2, NC>(a, pairs, li, wfix); break;
                 case 3: pair_reds<3, NC>(a, pairs, li, wfix); break;
                 case 4: pair_reds<4, NC>(a, pairs, li, wfix); break;
@@ -336,109 +337,146 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
         }
         __syncwarp();
 
-        // ---- dense z block: 8 k-steps of 4 rows, one DMMA each: A = z, B = w z (already in shared memory); the narrow
-        // categoricals' H[level, z] tiles reuse B with A = one-hot(level) ---------------------------------------------
+        // ---- dense z block: 8 k-steps of 4 rows, one DMMA each: A = z, B = b; the narrow categoricals' tiles reuse B
+        // with A = one-hot(level).  The 4 rows of a k-step are 2 apart: with the 10-double pitch of b a half-warp's 16
+        // operands then fall into 16 different bank pairs (consecutive rows collide: r02 ncu, 4 wavefronts instead of 2).
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-            // the 4 rows of a k-step are 2 apart: with the 10-double row pitch of (w z', r) a half-warp's 16 operands then
-            // fall into 16 different bank pairs (consecutive rows collide: r02 ncu, 4 wavefronts per load instead of 2)
-            const int src = 8 * (ks >> 1) + (ks & 1) + 2 * (lane & 3);
+            const int base = 8 * (ks >> 1) + (ks & 1);
+            const int src = base + 2 * (lane & 3);
             double zz = 1.0;
             if (jcol > 0) zz = (jcol - 1 < n_num) ? zs[src * n_num + jcol - 1] : 0.0;
-            const double bw = wz[src * kWzPitch + jcol];
+            const double bw = bs[src * kBPitch + jcol];
             dmma884(dz0, dz1, zz, bw);
 #pragma unroll
             for (int t = 0; t < NTILE; ++t) {
                 int o;
-                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(tile_to[t] + (uint32_t)(8 * (ks >> 1) + (ks & 1)) * (kToPitch * 4u)));
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(o) : "r"(tile_to[t] + (uint32_t)base * 4u));
                 dmma884(td0[t], td1[t], (o == tile_cmp[t]) ? 1.0 : 0.0, bw);
             }
         }
 
-        // ---- level blocks: scatter-add into the warp's table, two rows per step ------------------------------------
-        // Lane (c, j) always owns column j of categorical c's levels, so successive rows that hit the same level are
-        // ordered by program order of ONE thread; inside a row pair the second row's sum is forwarded in registers.
-        // All loads of a pair (both rounds: their slots are disjoint) are issued before its stores.
-        uint32_t pa[ROUNDS], pb[ROUNDS];
-        double va[ROUNDS], vb[ROUNDS];
-        auto load_pair = [&](int rp) {   // table addresses and addends of rows 2 rp, 2 rp + 1 for this lane's slots
-            const uint32_t ra_t = (uint32_t)(2 * rp) * (kToPitch * 4u), ra_w = (uint32_t)(2 * rp) * (kWzPitch * 8u);
-#pragma unroll
-            for (int q = 0; q < ROUNDS; ++q) {
-                int oa, ob;
-                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(oa) : "r"(slot_to[q] + ra_t));
-                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(ob) : "r"(slot_to[q] + ra_t + kToPitch * 4u));
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(va[q]) : "r"(slot_wz[q] + ra_w));
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(vb[q]) : "r"(slot_wz[q] + ra_w + kWzPitch * 8u));
-                pa[q] = slot_tb[q] + (uint32_t)oa;
-                pb[q] = slot_tb[q] + (uint32_t)ob;
+        // ---- wide categoricals: scatter-add b into the warp's tables, two rows per step ---------------------------
+        if (ROUNDS > 0) {
+            // turns on the pair's tables: even warp's group gi, odd warp's group gi, even warp's group gi + 1, ... — a fixed
+            // order, so the sums do not depend on timing
+            if (paired) {
+                if (warp & 1) mbar_wait(turn, (uint32_t)gi & 1u);
+                else if (gi > 0 && gi - 1 < mate_groups) mbar_wait(turn + 8, (uint32_t)(gi - 1) & 1u);
             }
-        };
-        load_pair(0);
+            int2 to[ROUNDS > 0 ? ROUNDS : 1];
+            double xb;
+            auto load_rows = [&](int rp) {   // offsets of rows 2 rp, 2 rp + 1 for this lane's categoricals; this lane's addend
 #pragma unroll
-        for (int rp = 0; rp < 16; ++rp) {
-            uint32_t ca[ROUNDS], cb[ROUNDS];
-            double ta[ROUNDS], tb[ROUNDS], xa[ROUNDS], xb[ROUNDS];
+                for (int q = 0; q < ROUNDS; ++q)
+                    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(to[q].x), "=r"(to[q].y) : "r"(sc_to[q] + 8u * rp));
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(xb) : "r"(sc_b + (uint32_t)rp * (2u * kBPitch * 8u)));
+            };
+            load_rows(0);
 #pragma unroll
-            for (int q = 0; q < ROUNDS; ++q) {
-                ca[q] = pa[q]; cb[q] = pb[q]; xa[q] = va[q]; xb[q] = vb[q];
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ta[q]) : "r"(ca[q]) : "memory");
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(tb[q]) : "r"(cb[q]) : "memory");
+            for (int rp = 0; rp < 16; ++rp) {
+                uint32_t addr[ROUNDS > 0 ? ROUNDS : 1];
+                bool clash = false;
+#pragma unroll
+                for (int q = 0; q < ROUNDS; ++q) {
+                    addr[q] = tab_u32 + (uint32_t)(half ? to[q].y : to[q].x) + 8u * colj;
+                    clash = clash || (sc_on[q] && to[q].x == to[q].y);
+                }
+                const double x = xb;
+                if (!__any_sync(0xffffffffu, clash)) {
+                    double t[ROUNDS > 0 ? ROUNDS : 1];
+#pragma unroll
+                    for (int q = 0; q < ROUNDS; ++q)
+                        if (sc_on[q]) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t[q]) : "r"(addr[q]) : "memory");
+                    if (rp + 1 < 16) load_rows(rp + 1);   // the row scratch is not written inside this loop
+#pragma unroll
+                    for (int q = 0; q < ROUNDS; ++q)
+                        if (sc_on[q]) asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr[q]), "d"(t[q] + x) : "memory");
+                } else {   // the two rows share a level somewhere: first row, then second row
+                    if (rp + 1 < 16) load_rows(rp + 1);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        if (half == hh) {
+#pragma unroll
+                            for (int q = 0; q < ROUNDS; ++q) {
+                                if (sc_on[q]) {
+                                    double t;
+                                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(addr[q]) : "memory");
+                                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr[q]), "d"(t + x) : "memory");
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();   // the next step's rows may hit the levels other lanes have just written
             }
-            if (rp + 1 < 16) load_pair(rp + 1);   // the row scratch is not written inside this loop: safe to read ahead
-#pragma unroll
-            for (int q = 0; q < ROUNDS; ++q) {
-                const double na = ta[q] + xa[q];
-                const double nb = ((ca[q] == cb[q]) ? na : tb[q]) + xb[q];
-                asm volatile("st.shared.f64 [%0], %1;" ::"r"(ca[q]), "d"(na) : "memory");
-                asm volatile("st.shared.f64 [%0], %1;" ::"r"(cb[q]), "d"(nb) : "memory");
+            if (paired && lane == 0) {
+                if (warp & 1) { if (gi + 1 < mate_groups) mbar_arrive(turn + 8); }
+                else if (gi < mate_groups) mbar_arrive(turn);
             }
         }
         __syncwarp();  // the stage and the row scratch are re-filled by the next iteration
     }
     cp_async_wait<0>();
-    // the DMMA tiles' sums go where the scatter would have put them (those cells were never touched)
-#pragma unroll
-    for (int t = 0; t < NTILE; ++t) {
-        if (t < a.ntiles && (lane >> 2) < a.tile_nlev[t]) {
-            double* cell = tab + (a.tile_lev0[t] + (lane >> 2)) * kTabPitch + 2 * (lane & 3);
-            cell[0] = td0[t];
-            cell[1] = td1[t];
-        }
-    }
 
     // ---- CTA reduction in a fixed warp order, straight into the workspace partial ----------------------------------
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) gz[j] += shfl_xor_f64(gz[j], m);
-    }
-#pragma unroll
     for (int m = 16; m >= 1; m >>= 1) ll += shfl_xor_f64(ll, m);
-    __syncthreads();  // every warp is done with its ring: reuse stage 0 of each ring for the small per-warp results
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) sw += shfl_xor_f64(sw, m);
+    __syncthreads();  // every warp is done with its ring: reuse it for the small per-warp results
     {
-        double* sm = reinterpret_cast<double*>(ring);  // Dz 64 | gz 8 | ll
+        // Dz 64 (row i = z_i, column 0 = g[z_i], column j >= 1 = H[z_i, z_j]) | ll at 72 | tiles [ntiles][8][8] from 80
+        double* sm = reinterpret_cast<double*>(ring);
         const int di = lane >> 2, dj = 2 * (lane & 3);
         sm[di * 8 + dj] = dz0;
         sm[di * 8 + dj + 1] = dz1;
-        if (lane < 8) {
-            double v = gz[0];
-#pragma unroll
-            for (int j = 1; j < 8; ++j) v = (lane == j) ? gz[j] : v;
-            sm[64 + lane] = v;
-        }
         if (lane == 8) sm[72] = ll;
+        if (lane == 9) sm[73] = sw;
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t) {
+            sm[80 + t * 64 + di * 8 + dj] = td0[t];
+            sm[80 + t * 64 + di * 8 + dj + 1] = td1[t];
+        }
     }
     __syncthreads();
     double* out = a.part_d + (size_t)blockIdx.x * a.stride_d;
-    for (int i = threadIdx.x; i < 80 + tab_doubles; i += blockDim.x) {
-        double v = 0.0;
-        if (i < 73) {
-            for (int wv = 0; wv < nwarps; ++wv) v += reinterpret_cast<const double*>(smem_raw + (size_t)wv * per_warp)[i];
+    for (int i = threadIdx.x; i < 80 + a.Lpad * kTabPitch; i += blockDim.x) {
+        // where entry i of the partial lives in a warp's block: a double index, or -1 for a structural zero
+        int srci = -1;
+        bool in_tab = false;
+        if (i < 64) {
+            const int u1 = i >> 3, u2 = i & 7;            // the assembly reads u1 <= u2 only
+            if (i == 0) srci = 73;                        // sum w
+            else if (u2 >= 1 && u1 <= u2) srci = u1 * 8 + u2;
+        } else if (i < 72) {
+            srci = (i - 64) * 8;                          // g[z_i] = column 0
+        } else if (i == 72) {
+            srci = 72;
         } else if (i >= 80) {
-            for (int wv = 0; wv < nwarps; ++wv)
-                v += reinterpret_cast<const double*>(smem_raw + (size_t)wv * per_warp + kCatStages * kStageBytes +
-                                                     kRowScratch)[i - 80];
+            const int level = (i - 80) / kTabPitch, col = (i - 80) - level * kTabPitch;
+            if (level < a.Ltot && col >= 1 && (col == 8 || col <= n_num)) {
+                int c = 0;
+                while (c + 1 < n_cat && level >= a.cat_lo[c + 1]) ++c;
+                const int code = level - a.cat_lo[c], jj = col == 8 ? 0 : col;
+                if (a.cat_wide[c] >= 0) {
+                    srci = (a.cat_tab[c] + code * 128) / 8 + jj;
+                    in_tab = true;
+                } else {
+                    for (int t = 0; t < a.ntiles; ++t)
+                        if (a.tile_lev0[t] <= level && level < a.tile_lev0[t] + a.tile_nlev[t])
+                            srci = 80 + t * 64 + (level - a.tile_lev0[t]) * 8 + jj;
+                }
+            }
+        }
+        double v = 0.0;
+        if (srci >= 0) {
+            if (!in_tab)
+                for (int wv = 0; wv < nwarps; ++wv)
+                    v += reinterpret_cast<const double*>(smem_raw + (size_t)wv * a.front_bytes)[srci];
+            else
+                for (int pr = 0; pr < npair; ++pr) v += reinterpret_cast<const double*>(tab_all + (size_t)pr * a.tab_bytes)[srci];
         }
         out[i] = v;
     }
@@ -466,6 +504,26 @@ __global__ void irls_cat_finalize_kernel(const CatArgs a, double* __restrict__ g
         while (c + 1 < a.n_cat && level >= a.cat_lo[c + 1]) ++c;
         return c;
     };
+    // sum of w over the rows at a level = the level's row (or column) of the pair block with its partner column, sinks
+    // included; exact integer sums per slice, converted per slice (a slice sum is < 2^63, the partition sum may not be)
+    auto level_weight = [&](int level) {
+        const int c = cat_of(level), d = a.partner[c];
+        const int code1 = level - a.cat_lo[c] + 1;
+        double v = 0.0;
+        for (int sl = 0; sl < a.S; ++sl) {
+            const unsigned long long* ps = pi + sl * a.stride_i;
+            long long acc = 0;
+            if (c < d) {
+                const unsigned long long* row = ps + a.pair_off[c * kCatMaxC + d] + code1 * a.pair_ld[d];
+                for (int j = 0; j < a.pair_ld[d]; ++j) acc += (long long)row[j];
+            } else {
+                const unsigned long long* col = ps + a.pair_off[d * kCatMaxC + c] + code1;
+                for (int j = 0; j < a.pair_ld[d]; ++j) acc += (long long)col[j * a.pair_ld[c]];
+            }
+            v += (double)acc * (1.0 / kWScale);
+        }
+        return v;
+    };
     double* Hk = H + (size_t)k * p * p;
     for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
         const int o1 = e / p, o2 = e - o1 * p;
@@ -475,18 +533,20 @@ __global__ void irls_cat_finalize_kernel(const CatArgs a, double* __restrict__ g
         double v = 0.0;
         if (u2 < 8) {
             for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + u1 * 8 + u2];
+        } else if (u1 == 0) {
+            v = level_weight(u2 - 8);
         } else if (u1 < 8) {
             for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + 80 + (u2 - 8) * kTabPitch + u1];
         } else {
             const int l1 = u1 - 8, l2 = u2 - 8;
             if (l1 == l2) {
-                for (int sl = 0; sl < a.S; ++sl) v += pd[sl * a.stride_d + 80 + l1 * kTabPitch];
+                v = level_weight(l1);
             } else {
                 const int c1 = cat_of(l1), c2 = cat_of(l2);
                 if (c1 != c2) {
                     const int idx = a.pair_off[c1 * kCatMaxC + c2] + (l1 - a.cat_lo[c1] + 1) * a.pair_ld[c2] +
                                     (l2 - a.cat_lo[c2] + 1);
-                    for (int sl = 0; sl < a.S; ++sl)  // per-slice conversion: a slice sum is < 2^63, the partition sum may not be
+                    for (int sl = 0; sl < a.S; ++sl)  // per-slice conversion, as above
                         v += (double)(long long)pi[sl * a.stride_i + idx] * (1.0 / kWScale);
                 }
             }
@@ -515,6 +575,10 @@ struct CatPlan {
     int Ltot, Lpad, npairs, S, warps;
     int64_t stride_d, stride_i;
     size_t bytes_d, bytes_i, smem;
+    // layout of the level work (see CatArgs)
+    int n_wide, rounds, ntiles, tab_bytes, stage_bytes, front_bytes, share_tables;
+    int cat_wide[kCatMaxC], cat_row[kCatMaxC], cat_tab[kCatMaxC], cat_sink[kCatMaxC];
+    int tile_row[kCatMaxTiles], tile_code0[kCatMaxTiles], tile_nlev[kCatMaxTiles], tile_lev0[kCatMaxTiles];
 };
 
 int cat_sm_count() {
@@ -528,13 +592,16 @@ int cat_sm_count() {
     return sms;
 }
 
-void cat_plan(int K, int n_cat, const int* n_levels, int64_t max_part_rows, CatPlan& pl) {
+void cat_plan(int K, int n_num, int n_cat, const int* n_levels, int64_t max_part_rows, CatPlan& pl) {
     pl.Ltot = 0;
     pl.npairs = 0;
+    int cat_lo[kCatMaxC];
     for (int c = 0; c < n_cat; ++c) {
         for (int d = 0; d < c; ++d) pl.npairs += (n_levels[d] + 1) * (n_levels[c] + 1);  // + sink row and column
+        cat_lo[c] = pl.Ltot;
         pl.Ltot += n_levels[c];
     }
+    if (n_cat == 1) pl.npairs = n_levels[0] + 1;  // the block with the empty partner column
     pl.Lpad = (pl.Ltot + 7) / 8 * 8;
     const int sms = cat_sm_count();
     // slices per partition: one CTA per SM at a time, so K * S should fill whole waves of `sms` CTAs (K = 120, S = 1 leaves
@@ -559,22 +626,96 @@ void cat_plan(int K, int n_cat, const int* n_levels, int64_t max_part_rows, CatP
     pl.stride_i = pl.npairs;
     pl.bytes_d = (size_t)K * S * pl.stride_d * 8;
     pl.bytes_i = (size_t)K * S * pl.stride_i * 8;
-    // as many warps as shared memory allows (each owns a ring, a row scratch and a level table)
-    const size_t per_warp = (size_t)kCatStages * kStageBytes + kRowScratch +
-                            (size_t)((((pl.Lpad + 1) * kTabPitch + 1) & ~1)) * 8;
-    const size_t fixed = (size_t)(8 + pl.Lpad) * 8;
+
+    // narrow categoricals (<= 16 levels, narrowest first, <= tile_budget tiles in total) go to DMMA tiles, the others are
+    // scattered, two per table: widest with second widest, and so on (a table has max(L, L') + 1 rows of 128 bytes)
+    static const int tile_budget = [] {
+        const char* e = getenv("DLSA_CAT_DMMA_TILES");
+        int v = e ? atoi(e) : kCatMaxTiles;
+        return v < 0 ? 0 : (v > kCatMaxTiles ? kCatMaxTiles : v);
+    }();
+    bool narrow[kCatMaxC] = {};
+    pl.ntiles = 0;
+    int n_narrow = 0;
+    for (;;) {
+        int pick = -1;
+        for (int c = 0; c < n_cat; ++c)
+            if (!narrow[c] && n_levels[c] >= 1 && n_levels[c] <= 16 && (pick < 0 || n_levels[c] < n_levels[pick])) pick = c;
+        if (pick < 0 || pl.ntiles + (n_levels[pick] + 7) / 8 > tile_budget) break;
+        narrow[pick] = true;
+        ++n_narrow;
+        pl.ntiles += (n_levels[pick] + 7) / 8;
+    }
+    int wide[kCatMaxC];
+    pl.n_wide = 0;
+    for (int c = 0; c < n_cat; ++c)
+        if (!narrow[c]) wide[pl.n_wide++] = c;
+    for (int i = 1; i < pl.n_wide; ++i)  // insertion sort, widest first
+        for (int j = i; j > 0 && n_levels[wide[j]] > n_levels[wide[j - 1]]; --j) {
+            const int t = wide[j]; wide[j] = wide[j - 1]; wide[j - 1] = t;
+        }
+    pl.rounds = (pl.n_wide + 1) / 2;
+    pl.tab_bytes = 0;
+    for (int c = 0; c < kCatMaxC; ++c) pl.cat_wide[c] = -1, pl.cat_row[c] = 0, pl.cat_tab[c] = 0, pl.cat_sink[c] = 0;
+    for (int v = 0; v < pl.n_wide; ++v) {
+        const int c = wide[v], rq = v >> 1, which = v & 1;
+        const int rows = n_levels[wide[2 * rq]] + 1;   // the round's wider column + the sink row
+        if (which == 0 && v > 0) pl.tab_bytes += (n_levels[wide[2 * (rq - 1)]] + 1) * 128;
+        pl.cat_wide[c] = v;
+        pl.cat_row[c] = v;
+        pl.cat_tab[c] = pl.tab_bytes + which * 64;
+        pl.cat_sink[c] = pl.tab_bytes + (rows - 1) * 128 + which * 64;
+    }
+    if (pl.n_wide > 0) pl.tab_bytes += (n_levels[wide[2 * (pl.rounds - 1)]] + 1) * 128;
+    int t = 0, nrow = pl.n_wide;
+    for (int c = 0; c < n_cat; ++c) {
+        if (!narrow[c]) continue;
+        pl.cat_row[c] = nrow;
+        for (int b = 0; b < n_levels[c]; b += 8, ++t) {
+            pl.tile_row[t] = nrow;
+            pl.tile_code0[t] = b;
+            pl.tile_nlev[t] = n_levels[c] - b < 8 ? n_levels[c] - b : 8;
+            pl.tile_lev0[t] = cat_lo[c] + b;
+        }
+        ++nrow;
+    }
+    for (; t < kCatMaxTiles; ++t) pl.tile_row[t] = 0, pl.tile_code0[t] = 0, pl.tile_nlev[t] = 0, pl.tile_lev0[t] = 0;
+
+    // as many warps as shared memory allows (each owns a ring, a row scratch and its level tables)
+    // (the ring + row scratch also stage the warp's small results at the end: 80 + 64 per tile doubles)
+    pl.stage_bytes = 256 * n_num + 128 * n_cat + 256;
+    pl.front_bytes = kCatStages * pl.stage_bytes + 32 * kBPitch * 8 + 128 * n_cat;
+    if (pl.front_bytes < (80 + 64 * kCatMaxTiles) * 8) pl.front_bytes = (80 + 64 * kCatMaxTiles) * 8;
+    const size_t fixed = (size_t)(8 + pl.Lpad) * 8 + 16 * (kCatMaxWarps / 2);
     const size_t budget = 227 * 1024;
-    int warps = (int)((budget - fixed) / per_warp);
-    if (warps > kCatMaxWarps) warps = kCatMaxWarps;
+    auto smem_for = [&](int w, int share) {
+        return (size_t)w * pl.front_bytes + (size_t)(share ? (w + 1) / 2 : w) * pl.tab_bytes + fixed;
+    };
+    int w_own = kCatMaxWarps, w_pair = kCatMaxWarps;
+    while (w_own > 1 && smem_for(w_own, 0) > budget) --w_own;
+    while (w_pair > 1 && smem_for(w_pair, 1) > budget) --w_pair;
+    // measured on the airline shape (r02): 12 warps with own tables 9.98 ms, 16 warps in pairs 9.54 ms, 14 in pairs 10.5 ms —
+    // taking turns costs about as much as two warps
+    static const int share_env = [] {
+        const char* e = getenv("DLSA_CAT_SHARE_TABLES");
+        return e ? atoi(e) : -1;
+    }();
+    pl.share_tables = share_env >= 0 ? (share_env != 0) : (pl.tab_bytes > 0 && w_pair >= w_own + 4);
+    int warps = pl.share_tables ? w_pair : w_own;
+    static const int warp_cap = [] {
+        const char* e = getenv("DLSA_CAT_WARPS");
+        return e ? atoi(e) : kCatMaxWarps;
+    }();
+    if (warps > warp_cap && warp_cap >= 4) warps = warp_cap;
     pl.warps = warps;
-    pl.smem = (size_t)warps * per_warp + fixed;
+    pl.smem = smem_for(warps, pl.share_tables);
 }
 
 }  // namespace
 
 size_t irls_cat_workspace_bytes(int K, int n_cat, const int* n_levels, int64_t max_part_rows) {
     CatPlan pl;
-    cat_plan(K, n_cat, n_levels, max_part_rows, pl);
+    cat_plan(K, 0, n_cat, n_levels, max_part_rows, pl);   // the partial buffers do not depend on the numeric columns
     return pl.bytes_d + pl.bytes_i + 256;
 }
 
@@ -592,7 +733,7 @@ int irls_cat_launch(const double* numeric, int64_t ldn, int n_num, const double*
                     const double* beta, const int* active, double* g, double* H, double* loglik, int64_t max_part_rows,
                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
     CatPlan pl;
-    cat_plan(K, n_cat, n_levels, max_part_rows, pl);
+    cat_plan(K, n_num, n_cat, n_levels, max_part_rows, pl);
     DLSA_REQUIRE(pl.Ltot <= 192, DLSA_E_UNSUPPORTED, "categorical pass: %d levels in total (max 192)", pl.Ltot);
     DLSA_REQUIRE(pl.warps >= 4, DLSA_E_UNSUPPORTED, "categorical pass: level tables do not fit shared memory");
     const size_t need = pl.bytes_d + pl.bytes_i + 256;
@@ -604,6 +745,7 @@ int irls_cat_launch(const double* numeric, int64_t ldn, int n_num, const double*
     a.n_num = n_num;
     a.codes = codes;
     a.n_cat = n_cat;
+    a.n_pair_cats = n_cat < 2 ? 2 : n_cat;
     a.mean = mean;
     a.sd = sd;
     a.y = y;
@@ -618,6 +760,7 @@ int irls_cat_launch(const double* numeric, int64_t ldn, int n_num, const double*
     a.Lpad = pl.Lpad;
     a.npairs = pl.npairs;
     int lo = 0, off = 0;
+    for (int c = 0; c < kCatMaxC; ++c) a.pair_ld[c] = 1;
     for (int c = 0; c < n_cat; ++c) {
         a.cat_lo[c] = lo;
         for (int d = 0; d < c; ++d) {
@@ -628,79 +771,56 @@ int irls_cat_launch(const double* numeric, int64_t ldn, int n_num, const double*
         lo += n_levels[c];
     }
     for (int c = n_cat; c <= kCatMaxC; ++c) a.cat_lo[c] = lo;
+    for (int c = 0; c < n_cat; ++c) {  // partner = the other column with the fewest levels (a lone column: the empty one)
+        int d = -1;
+        for (int e = 0; e < n_cat; ++e)
+            if (e != c && (d < 0 || n_levels[e] < n_levels[d])) d = e;
+        a.partner[c] = d < 0 ? 1 : d;
+    }
     const uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
     a.part_d = reinterpret_cast<double*>(base);
     a.part_i = reinterpret_cast<unsigned long long*>(base + pl.bytes_d);
     a.stride_d = pl.stride_d;
     a.stride_i = pl.stride_i;
     DLSA_CUDA(cudaMemsetAsync(a.part_i, 0, pl.bytes_i, st));
-    // narrow categoricals (<= 16 levels, narrowest first, <= kCatMaxTiles tiles in total) go to DMMA tiles; the others —
-    // and every g column — to the scatter slots
-    static const int tile_budget = [] {
-        const char* e = getenv("DLSA_CAT_DMMA_TILES");
-        int v = e ? atoi(e) : kCatMaxTiles;
-        return v < 0 ? 0 : (v > kCatMaxTiles ? kCatMaxTiles : v);
-    }();
-    bool on_dmma[kCatMaxC] = {};
-    for (;;) {
-        int best = -1;
-        for (int c = 0; c < n_cat; ++c)
-            if (!on_dmma[c] && n_levels[c] >= 1 && n_levels[c] <= 16 && (best < 0 || n_levels[c] < n_levels[best])) best = c;
-        if (best < 0 || a.ntiles + (n_levels[best] + 7) / 8 > tile_budget) break;
-        on_dmma[best] = true;
-        for (int b = 0; b < n_levels[best]; b += 8) {
-            a.tile_cat[a.ntiles] = best;
-            a.tile_lev0[a.ntiles] = a.cat_lo[best] + b;
-            a.tile_nlev[a.ntiles] = n_levels[best] - b < 8 ? n_levels[best] - b : 8;
-            ++a.ntiles;
-        }
+    a.n_wide = pl.n_wide;
+    a.tab_bytes = pl.tab_bytes;
+    a.share_tables = pl.share_tables;
+    a.stage_bytes = pl.stage_bytes;
+    a.front_bytes = pl.front_bytes;
+    a.ntiles = pl.ntiles;
+    for (int c = 0; c < kCatMaxC; ++c) {
+        a.cat_wide[c] = pl.cat_wide[c];
+        a.cat_row[c] = pl.cat_row[c];
+        a.cat_tab[c] = pl.cat_tab[c];
+        a.cat_sink[c] = pl.cat_sink[c];
     }
-    // Slot layout: 64-bit shared accesses are served one HALF-warp at a time, so a scattered categorical's 2 + n_num
-    // columns (one run of consecutive doubles in its level's row) are kept inside one half-warp and the single g
-    // columns of the DMMA categoricals fill the gaps — two runs in one half-warp always overlap in some bank.
-    {
-        const int run = n_num + 2;                   // w | w z_1..n_num | r
-        int fill[6] = {0, 0, 0, 0, 0, 0};            // lanes used per half-warp (3 rounds x 2)
-        unsigned char lay[96];
-        for (int i = 0; i < 96; ++i) lay[i] = 0x89;  // idle: categorical 8 (always the sink row), column 9 (always 0.0)
-        auto place = [&](int c, int j0, int cnt, bool r_col) -> bool {
-            for (int h = 0; h < 6; ++h) {
-                if (fill[h] + cnt + (r_col ? 1 : 0) > 16) continue;
-                for (int j = 0; j < cnt; ++j) lay[16 * h + fill[h]++] = (unsigned char)(c * 16 + j0 + j);
-                if (r_col) lay[16 * h + fill[h]++] = (unsigned char)(c * 16 + 8);
-                return true;
-            }
-            return false;
-        };
-        bool ok = true;
-        for (int c = 0; c < n_cat && ok; ++c)
-            if (!on_dmma[c]) ok = place(c, 0, run - 1, true);
-        for (int c = 0; c < n_cat && ok; ++c)
-            if (on_dmma[c]) ok = place(c, 8, 1, false);
-        if (ok) {
-            int last = 0;
-            for (int h = 0; h < 6; ++h)
-                if (fill[h] > 0) last = 16 * h + 16;
-            a.nslots = last;
-            for (int i = 0; i < last; ++i) a.slot[i] = lay[i];
-        } else {  // more runs than half-warps (7+ scattered categoricals): dense packing, 9 n_cat <= 72 slots always fit
-            a.nslots = 0;
-            for (int c = 0; c < n_cat; ++c)
-                if (!on_dmma[c])
-                    for (int j = 0; j <= n_num; ++j) a.slot[a.nslots++] = (unsigned char)(c * 16 + j);
-            for (int c = 0; c < n_cat; ++c) a.slot[a.nslots++] = (unsigned char)(c * 16 + 8);
-        }
+    for (int t = 0; t < kCatMaxTiles; ++t) {
+        a.tile_row[t] = pl.tile_row[t];
+        a.tile_code0[t] = pl.tile_code0[t];
+        a.tile_nlev[t] = pl.tile_nlev[t];
+        a.tile_lev0[t] = pl.tile_lev0[t];
     }
-    const int rounds = (a.nslots + 31) / 32;  // 1..3
-    const int ntile = (a.ntiles + 1) & ~1;
+    const int rounds = pl.rounds;              // 0..4
+    const int ntile = (pl.ntiles + 1) & ~1;    // 0, 2, 4, 6
     const bool c4 = n_cat <= 4;
     int rc = DLSA_E_UNSUPPORTED;
-#define DLSA_CAT_CASE(R, T)                                                                     \
-    if (rounds == R && ntile == T) rc = c4 ? cat_launch_t<R, 4, T>(a, pl, st) : cat_launch_t<R, 8, T>(a, pl, st);
-    DLSA_CAT_CASE(1, 0) DLSA_CAT_CASE(1, 2) DLSA_CAT_CASE(1, 4) DLSA_CAT_CASE(1, 6)
-    DLSA_CAT_CASE(2, 0) DLSA_CAT_CASE(2, 2) DLSA_CAT_CASE(2, 4) DLSA_CAT_CASE(2, 6)
-    DLSA_CAT_CASE(3, 0) DLSA_CAT_CASE(3, 2) DLSA_CAT_CASE(3, 4) DLSA_CAT_CASE(3, 6)
-#undef DLSA_CAT_CASE
+#define DLSA_CAT_CASE4(R, T) \
+    if (c4 && rounds == R && ntile == T) rc = cat_launch_t<R, 4, T>(a, pl, st);
+#define DLSA_CAT_CASE8(R, T) \
+    if (!c4 && rounds == R && ntile == T) rc = cat_launch_t<R, 8, T>(a, pl, st);
+    DLSA_CAT_CASE4(0, 2) DLSA_CAT_CASE4(0, 4) DLSA_CAT_CASE4(0, 6)
+    DLSA_CAT_CASE4(1, 0) DLSA_CAT_CASE4(1, 2) DLSA_CAT_CASE4(1, 4) DLSA_CAT_CASE4(1, 6)
+    DLSA_CAT_CASE4(2, 0) DLSA_CAT_CASE4(2, 2) DLSA_CAT_CASE4(2, 4) DLSA_CAT_CASE4(2, 6)
+    DLSA_CAT_CASE8(0, 6)
+    DLSA_CAT_CASE8(1, 4) DLSA_CAT_CASE8(1, 6)
+    DLSA_CAT_CASE8(2, 2) DLSA_CAT_CASE8(2, 4) DLSA_CAT_CASE8(2, 6)
+    DLSA_CAT_CASE8(3, 0) DLSA_CAT_CASE8(3, 2) DLSA_CAT_CASE8(3, 4) DLSA_CAT_CASE8(3, 6)
+    DLSA_CAT_CASE8(4, 0) DLSA_CAT_CASE8(4, 2) DLSA_CAT_CASE8(4, 4) DLSA_CAT_CASE8(4, 6)
+#undef DLSA_CAT_CASE4
+#undef DLSA_CAT_CASE8
+    DLSA_REQUIRE(rc != DLSA_E_UNSUPPORTED, DLSA_E_UNSUPPORTED, "categorical pass: no kernel for %d scatter rounds x %d tiles",
+                 rounds, ntile);
     if (rc != 0) return rc;
     irls_cat_finalize_kernel<<<K, 256, 0, st>>>(a, g, H, loglik);
     count_launch();
