@@ -85,13 +85,23 @@ __device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, d
     double* P = W + kNB * kPPitch;
     if (tid == 0) *ok_s = 1;
     __syncthreads();
+    const int pcap = (p + 31) >> 5;   // 32-row blocks P has room for
     for (int kb = 0; kb < p; kb += kNB) {
         const int nb = (p - kb < kNB) ? (p - kb) : kNB;
         const int rows_total = p - kb;                 // rows of the panel, the diagonal block first
         const int nrb = (rows_total + 31) >> 5;
-        // (1) panel update on DMMA: 32 rows x 32 columns per warp and turn, k over the finished columns 0..kb-1
-        for (int b = warp; b < nrb; b += nwarps) {
+        // (1) panel update on DMMA: 32 rows x 32 columns per warp and turn, k over the finished columns 0..kb-1.  Late panels
+        // have few row blocks and long k loops: the k range is then SPLIT over the idle warps (nsp parts per block), the
+        // partial products parked in the unused rows of P and summed in a fixed order afterwards.
+        const int kiters = kb >> 3;
+        int nsp = nwarps / nrb;
+        if (nsp > pcap / nrb) nsp = pcap / nrb;
+        if (nsp > (kiters >> 1)) nsp = kiters >> 1;
+        if (nsp < 1) nsp = 1;
+        for (int wi = warp; wi < nrb * nsp; wi += nwarps) {
+            const int b = wi % nrb, sp = wi / nrb;
             const int r0 = kb + 32 * b;
+            const int k_lo = ((kiters * sp) / nsp) << 3, k_hi = ((kiters * (sp + 1)) / nsp) << 3;
             double c0[4][4], c1[4][4];
 #pragma unroll
             for (int ti = 0; ti < 4; ti++)
@@ -108,7 +118,7 @@ __device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, d
                 bo[t] = (bok[t] ? rb : p - 1) * ld + 2 * q;
             }
 #pragma unroll 1
-            for (int kk = 0; kk < kb; kk += 8) {
+            for (int kk = k_lo; kk < k_hi; kk += 8) {
                 double2 ac[4], bc[4];
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
@@ -127,24 +137,47 @@ __device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, d
                         dmma884(c0[ti][tj], c1[ti][tj], ac[ti].y, bc[tj].y);
                     }
             }
-            // U = A - (L L')  ->  P; entries above the diagonal of the diagonal block are never read
+            // U = A - (L L')  ->  P; entries above the diagonal of the diagonal block are never read.  With a split k range
+            // the partial product goes to block sp * nrb + b of P instead and U is formed below.
 #pragma unroll
             for (int ti = 0; ti < 4; ti++) {
                 const int r = r0 + 8 * ti + a8;
 #pragma unroll
                 for (int tj = 0; tj < 4; tj++) {
                     const int c = kb + 8 * tj + 2 * q;
-                    double v0 = 0.0, v1 = 0.0;
-                    if (r < p) {   // the entries of A are read here, once; L only ever holds finished columns
-                        if (c < kb + nb && c <= r) v0 = A[(size_t)r * p + c] - c0[ti][tj];
-                        if (c + 1 < kb + nb && c + 1 <= r) v1 = A[(size_t)r * p + c + 1] - c1[ti][tj];
+                    double v0 = c0[ti][tj], v1 = c1[ti][tj];
+                    if (nsp == 1) {
+                        v0 = 0.0, v1 = 0.0;
+                        if (r < p) {   // the entries of A are read here, once; L only ever holds finished columns
+                            if (c < kb + nb && c <= r) v0 = A[(size_t)r * p + c] - c0[ti][tj];
+                            if (c + 1 < kb + nb && c + 1 <= r) v1 = A[(size_t)r * p + c + 1] - c1[ti][tj];
+                        }
                     }
-                    *reinterpret_cast<double2*>(P + (size_t)(32 * b + 8 * ti + a8) * kPPitch + 8 * tj + 2 * q) =
+                    *reinterpret_cast<double2*>(P + (size_t)(32 * (sp * nrb + b) + 8 * ti + a8) * kPPitch + 8 * tj + 2 * q) =
                         make_double2(v0, v1);
                 }
             }
         }
         __syncthreads();
+        if (nsp > 1) {
+            for (int e = tid; e < nrb * 32 * 16; e += nt) {   // (row of the panel, column pair)
+                const int rr = e >> 4, cp = (e & 15) << 1;
+                const int r = kb + rr, c = kb + cp;
+                double s0 = 0.0, s1 = 0.0;
+                for (int sp = 0; sp < nsp; sp++) {
+                    const double2 v = *reinterpret_cast<const double2*>(P + (size_t)(32 * sp * nrb + rr) * kPPitch + cp);
+                    s0 += v.x;
+                    s1 += v.y;
+                }
+                double v0 = 0.0, v1 = 0.0;
+                if (r < p) {
+                    if (c < kb + nb && c <= r) v0 = A[(size_t)r * p + c] - s0;
+                    if (c + 1 < kb + nb && c + 1 <= r) v1 = A[(size_t)r * p + c + 1] - s1;
+                }
+                *reinterpret_cast<double2*>(P + (size_t)rr * kPPitch + cp) = make_double2(v0, v1);
+            }
+            __syncthreads();
+        }
         // (2) diagonal block (rows 0..31 of P) -> D (identity beyond nb), factored by warp 0
         for (int e = tid; e < kNB * kNB; e += nt) {
             const int r = e >> 5, c = e & 31;
@@ -251,10 +284,12 @@ __device__ __forceinline__ void chol_blocked_solve_cta(const double* L, int ld, 
 #pragma unroll
             for (int j = 0; j < kNB; j++) lrow[j] = (lane < nb && j <= lane) ? L[(size_t)(kb + lane) * ld + kb + j] : 1.0;
             double xr = (lane < nb) ? x[kb + lane] : 0.0;
+            double rinv = 1.0;   // 1 / L[lane][lane]: one division per lane up front instead of one per step of the chain
+#pragma unroll
+            for (int j = 0; j < kNB; j++) rinv = (lane == j) ? 1.0 / lrow[j] : rinv;
 #pragma unroll
             for (int j = 0; j < kNB; j++) {
-                const double djj = __shfl_sync(0xffffffffu, lrow[j], j);
-                const double xj = __shfl_sync(0xffffffffu, xr, j) / djj;
+                const double xj = __shfl_sync(0xffffffffu, xr * rinv, j);
                 if (lane == j) xr = xj;
                 if (lane > j) xr = fma(-lrow[j], xj, xr);
             }
@@ -278,10 +313,12 @@ __device__ __forceinline__ void chol_blocked_solve_cta(const double* L, int ld, 
 #pragma unroll
             for (int j = 0; j < kNB; j++) lcol[j] = (j < nb && lane <= j) ? L[(size_t)(kb + j) * ld + kb + lane] : 1.0;
             double xr = (lane < nb) ? x[kb + lane] : 0.0;
+            double rinv = 1.0;
+#pragma unroll
+            for (int j = 0; j < kNB; j++) rinv = (lane == j) ? 1.0 / lcol[j] : rinv;
 #pragma unroll
             for (int j = kNB - 1; j >= 0; j--) {
-                const double djj = __shfl_sync(0xffffffffu, lcol[j], j);
-                const double xj = __shfl_sync(0xffffffffu, xr, j) / djj;
+                const double xj = __shfl_sync(0xffffffffu, xr * rinv, j);
                 if (lane == j) xr = xj;
                 if (lane < j && j < nb) xr = fma(-lcol[j], xj, xr);
             }
