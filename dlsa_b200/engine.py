@@ -644,6 +644,120 @@ def dlsa_fit(X, y, part_offsets, fit_intercept=False, sample_size=None, type="la
     return finish_fit(fits, fit_intercept, float(sample_size), type, group)
 
 
+# ---- pageable host memory: staged copies --------------------------------------------------------------------------------
+# cudaMemcpyAsync from PAGEABLE memory goes through the driver's own bounce buffer, single-threaded (measured on the bench
+# box: 11 GB/s against 55 GB/s from pinned memory).  A caller that holds numpy / pandas data cannot pin 40 GB in place, so
+# the host entries stage such inputs themselves: a few pinned slots, filled by a pool of host threads (torch's CPU copy
+# releases the GIL) while the previous slots cross PCIe.
+_STAGE_SLOTS = {}
+_STAGE_SLOT_BYTES = 256 << 20
+_STAGE_N_SLOTS = 4
+
+
+def _stage_slots(dev):
+    key = (dev.index, _STAGE_SLOT_BYTES, _STAGE_N_SLOTS)
+    if key not in _STAGE_SLOTS:
+        _STAGE_SLOTS[key] = [torch.empty(_STAGE_SLOT_BYTES, dtype=torch.uint8).pin_memory() for _ in range(_STAGE_N_SLOTS)]
+    return _STAGE_SLOTS[key]
+
+
+class _StagedCopies:
+    """Queues ``dst[r0:r1] <- src[r0:r1]`` for every (dst, src) pair and every row block of ``bounds`` on ``copy_stream``
+    from a background thread; ``wait(i, compute_stream)`` makes the compute stream wait for block i."""
+
+    def __init__(self, pairs, bounds, dev, copy_stream, workers=None):
+        import concurrent.futures
+        import os
+        import threading
+        self.pairs, self.bounds, self.dev, self.copy = pairs, bounds, dev, copy_stream
+        self.ready = [threading.Event() for _ in bounds]
+        self.events = [None] * len(bounds)
+        self.error = None
+        self.workers = workers or max(1, min(16, (os.cpu_count() or 2) - 1))
+        self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=self.workers)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _fill(self, view, src):
+        n = src.shape[0]
+        step = max(1, -(-n // self.workers))
+        futs = [self.pool.submit(lambda a, b: view[a:b].copy_(src[a:b]), a, min(n, a + step)) for a in range(0, n, step)]
+        for f in futs:
+            f.result()
+
+    def _run(self):
+        try:
+            torch.cuda.set_device(self.dev)
+            slots = _stage_slots(self.dev)
+            free = [None] * len(slots)   # the event after which a slot may be overwritten
+            turn = 0
+            with torch.cuda.stream(self.copy):
+                for i, (r0, r1) in enumerate(self.bounds):
+                    for dst, src in self.pairs:
+                        row_bytes = max(1, src[0:1].numel() * src.element_size())
+                        rows_per_slot = max(1, _STAGE_SLOT_BYTES // row_bytes)
+                        for a in range(r0, r1, rows_per_slot):
+                            b = min(r1, a + rows_per_slot)
+                            sl = turn % len(slots)
+                            turn += 1
+                            if free[sl] is not None:
+                                free[sl].synchronize()
+                            piece = src[a:b]
+                            view = slots[sl][: piece.numel() * piece.element_size()].view(piece.dtype).view(piece.shape)
+                            self._fill(view, piece)
+                            dst[a:b].copy_(view, non_blocking=True)
+                            ev = torch.cuda.Event()
+                            ev.record(self.copy)
+                            free[sl] = ev
+                    ev = torch.cuda.Event()
+                    ev.record(self.copy)
+                    self.events[i] = ev
+                    self.ready[i].set()
+        except BaseException as exc:  # surfaced by wait()
+            self.error = exc
+            for r in self.ready:
+                r.set()
+
+    def wait(self, i, compute_stream):
+        self.ready[i].wait()
+        if self.error is not None:
+            raise self.error
+        compute_stream.wait_event(self.events[i])
+
+    def close(self):
+        self.thread.join()
+        self.pool.shutdown(wait=True)
+        if self.error is not None:
+            raise self.error
+
+
+def _queue_host_copies(pairs, bounds, dev, compute):
+    """Host -> device copies of the row blocks ``bounds`` for every (dst, src) pair, on their own stream.  Returns an
+    object with ``wait(i, stream)`` and ``close()``.  Pinned sources are queued directly; pageable ones are staged."""
+    copy = torch.cuda.Stream(dev)
+    copy.wait_stream(compute)  # the buffers may still be in use by earlier work on the compute stream
+    if all(src.is_pinned() for _, src in pairs):
+        class _Direct:
+            def __init__(self):
+                self.events = []
+                with torch.cuda.stream(copy):
+                    for r0, r1 in bounds:
+                        for dst, src in pairs:
+                            dst[r0:r1].copy_(src[r0:r1], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy)
+                        self.events.append(ev)
+
+            def wait(self, i, stream):
+                stream.wait_event(self.events[i])
+
+            def close(self):
+                pass
+        return _Direct()
+    return _StagedCopies(pairs, bounds, dev, copy)
+
+
+
 def dlsa_fit_host(Xh: torch.Tensor, yh: torch.Tensor, part_offsets_host: torch.Tensor, fit_intercept=False,
                   sample_size=None, type="lar", config=None, group=None, device=None, n_groups: int = 16,
                   buffers=None):
@@ -670,29 +784,22 @@ def dlsa_fit_host(Xh: torch.Tensor, yh: torch.Tensor, part_offsets_host: torch.T
     G = max(1, min(int(n_groups), K))
     bounds = [(K * i) // G for i in range(G + 1)]
     compute = torch.cuda.current_stream(dev)
-    copy = torch.cuda.Stream(dev)
-    copy.wait_stream(compute)  # the buffers may still be in use by earlier work on the compute stream
-    events = []
-    with torch.cuda.stream(copy):
-        for i in range(G):
-            r0, r1 = offs[bounds[i]], offs[bounds[i + 1]]
-            Xd[r0:r1].copy_(Xh[r0:r1], non_blocking=True)
-            yd[r0:r1].copy_(yh[r0:r1], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy)
-            events.append(ev)
+    copies = _queue_host_copies([(Xd, Xh), (yd, yh)], [(offs[bounds[i]], offs[bounds[i + 1]]) for i in range(G)], dev, compute)
     parts = []
     pooled = None  # mean coefficients of the first fitted block: the warm start of every later block
-    for i in range(G):
-        k0, k1 = bounds[i], bounds[i + 1]
-        r0, r1 = offs[k0], offs[k1]
-        off_g = (part_offsets_host[k0:k1 + 1] - r0).to(dev, non_blocking=True)
-        compute.wait_event(events[i])
-        if k1 > k0:
-            parts.append(fit_logistic_partitions(Xd[r0:r1], yd[r0:r1], off_g, fit_intercept, config,
-                                                 pooled_start=pooled))
-            if pooled is None and K >= (config or EngineConfig()).warm_min_partitions:
-                pooled = _pooled_start(parts[-1])
+    try:
+        for i in range(G):
+            k0, k1 = bounds[i], bounds[i + 1]
+            r0, r1 = offs[k0], offs[k1]
+            off_g = (part_offsets_host[k0:k1 + 1] - r0).to(dev, non_blocking=True)
+            copies.wait(i, compute)
+            if k1 > k0:
+                parts.append(fit_logistic_partitions(Xd[r0:r1], yd[r0:r1], off_g, fit_intercept, config,
+                                                     pooled_start=pooled))
+                if pooled is None and K >= (config or EngineConfig()).warm_min_partitions:
+                    pooled = _pooled_start(parts[-1])
+    finally:
+        copies.close()
     fits = PartitionFits(coef=torch.cat([f.coef for f in parts]), Sig_inv=torch.cat([f.Sig_inv for f in parts]),
                          Sig_invMcoef=torch.cat([f.Sig_invMcoef for f in parts]),
                          status=torch.cat([f.status for f in parts]), iters=torch.cat([f.iters for f in parts]),
@@ -732,32 +839,25 @@ def dlsa_fit_host_cat(numeric_h: torch.Tensor, codes_h: torch.Tensor, n_levels, 
     G = max(1, min(int(n_groups), K))
     bounds = [(K * i) // G for i in range(G + 1)]
     compute = torch.cuda.current_stream(dev)
-    copy = torch.cuda.Stream(dev)
-    copy.wait_stream(compute)
-    events = []
-    with torch.cuda.stream(copy):
-        for i in range(G):
-            r0, r1 = offs[bounds[i]], offs[bounds[i + 1]]
-            nd[r0:r1].copy_(numeric_h[r0:r1], non_blocking=True)
-            cd[r0:r1].copy_(codes_h[r0:r1], non_blocking=True)
-            yd[r0:r1].copy_(yh[r0:r1], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy)
-            events.append(ev)
+    copies = _queue_host_copies([(nd, numeric_h), (cd, codes_h), (yd, yh)],
+                                [(offs[bounds[i]], offs[bounds[i + 1]]) for i in range(G)], dev, compute)
     parts = []
     pooled = None
-    for i in range(G):
-        k0, k1 = bounds[i], bounds[i + 1]
-        r0, r1 = offs[k0], offs[k1]
-        if k1 == k0:
-            continue
-        sizes_h = part_offsets_host[k0 + 1:k1 + 1] - part_offsets_host[k0:k1]
-        off_g = (part_offsets_host[k0:k1 + 1] - r0).to(dev, non_blocking=True)
-        compute.wait_event(events[i])
-        parts.append(fit_logistic_partitions_cat(nd[r0:r1], cd[r0:r1], n_levels, yd[r0:r1], off_g, fit_intercept, mean,
-                                                 std, config, pooled_start=pooled, max_part_rows=int(sizes_h.max())))
-        if pooled is None and len(parts) == 1 and G > 1:
-            pooled = _pooled_start(parts[0])
+    try:
+        for i in range(G):
+            k0, k1 = bounds[i], bounds[i + 1]
+            r0, r1 = offs[k0], offs[k1]
+            copies.wait(i, compute)
+            if k1 == k0:
+                continue
+            sizes_h = part_offsets_host[k0 + 1:k1 + 1] - part_offsets_host[k0:k1]
+            off_g = (part_offsets_host[k0:k1 + 1] - r0).to(dev, non_blocking=True)
+            parts.append(fit_logistic_partitions_cat(nd[r0:r1], cd[r0:r1], n_levels, yd[r0:r1], off_g, fit_intercept, mean,
+                                                     std, config, pooled_start=pooled, max_part_rows=int(sizes_h.max())))
+            if pooled is None and len(parts) == 1 and G > 1:
+                pooled = _pooled_start(parts[0])
+    finally:
+        copies.close()
     fits = PartitionFits(coef=torch.cat([f.coef for f in parts]), Sig_inv=torch.cat([f.Sig_inv for f in parts]),
                          Sig_invMcoef=torch.cat([f.Sig_invMcoef for f in parts]),
                          status=torch.cat([f.status for f in parts]), iters=torch.cat([f.iters for f in parts]),
