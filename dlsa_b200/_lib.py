@@ -57,6 +57,7 @@ SIGNATURES = {
     "dlsa_probe_fp64_dmma": (_i, [_i, _i, _vp, _vp, _vp]),
     "dlsa_onehot_expand_f64": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp, _i64, _vp]),
     "dlsa_irls_tiled_schedule": (_i, [_i, _i, _vp, _vp]),
+    "dlsa_irls_cat_plan": (_i, [_i, _i, _i, _vp, _i64, _vp, _vp, _vp]),
     "dlsa_column_stats_workspace_bytes": (_sz, [_i]),
     "dlsa_column_stats_f64": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _sz, _vp]),
 }

@@ -57,6 +57,8 @@ size_t colstats_workspace_bytes(int px);
 int colstats_launch(const double*, int64_t, int64_t, int, double*, double*, cudaStream_t);
 
 size_t irls_cat_workspace_bytes(int K, int n_cat, const int* n_levels, int64_t max_part_rows);
+int irls_cat_plan_info(int K, int n_num, int n_cat, const int* n_levels, int64_t max_part_rows, int* info, int* cat_out,
+                       int* tile_out);
 int irls_cat_launch(const double*, int64_t, int, const double*, const double*, const int*, int, const int*, const double*,
                     const int64_t*, int, int, const double*, const int*, double*, double*, double*, int64_t, void*,
                     size_t, cudaStream_t);
@@ -224,6 +226,14 @@ int dlsa_irls_tiled_schedule(int px, int fit_intercept, uint32_t* sched_out, int
     DLSA_REQUIRE(sched_out && info, DLSA_E_BADARG, "tiled schedule: null pointer");
     DLSA_REQUIRE(irls_tiled_schedule_info(px, fit_intercept ? 1 : 0, sched_out, info) == 0, DLSA_E_UNSUPPORTED,
                  "tiled schedule: p must be in 57..512");
+    return 0;
+}
+
+int dlsa_irls_cat_plan(int K, int n_num, int n_cat, const int* n_levels_host, int64_t max_part_rows, int* info,
+                       int* cat_out, int* tile_out) {
+    DLSA_REQUIRE(n_levels_host && info && cat_out && tile_out, DLSA_E_BADARG, "categorical plan: null pointer");
+    DLSA_REQUIRE(irls_cat_plan_info(K, n_num, n_cat, n_levels_host, max_part_rows, info, cat_out, tile_out) == 0,
+                 DLSA_E_UNSUPPORTED, "categorical plan: 1..8 categorical columns, 0..7 numeric columns");
     return 0;
 }
 

@@ -719,6 +719,33 @@ size_t irls_cat_workspace_bytes(int K, int n_cat, const int* n_levels, int64_t m
     return pl.bytes_d + pl.bytes_i + 256;
 }
 
+// Host-only: the layout cat_plan chooses, for tests.  info[12]: slices per partition, warps, tables shared by warp pairs,
+// wide categoricals, scatter rounds, DMMA tiles, table bytes (one set), ring stage bytes, front bytes, dynamic shared
+// memory, pair cells, padded levels.  cat_out [n_cat][4]: wide slot (-1 = narrow), scratch row, byte offset of level 0 in
+// the tables, byte offset of the sink.  tile_out [6][4]: scratch row, first code, live levels, first level (level space).
+int irls_cat_plan_info(int K, int n_num, int n_cat, const int* n_levels, int64_t max_part_rows, int* info, int* cat_out,
+                       int* tile_out) {
+    if (n_cat < 1 || n_cat > kCatMaxC || n_num < 0 || n_num > kCatMaxNum || K < 1) return -1;
+    CatPlan pl;
+    cat_plan(K, n_num, n_cat, n_levels, max_part_rows, pl);
+    const int v[12] = {pl.S, pl.warps, pl.share_tables, pl.n_wide, pl.rounds, pl.ntiles, pl.tab_bytes, pl.stage_bytes,
+                       pl.front_bytes, (int)pl.smem, pl.npairs, pl.Lpad};
+    for (int i = 0; i < 12; ++i) info[i] = v[i];
+    for (int c = 0; c < n_cat; ++c) {
+        cat_out[4 * c + 0] = pl.cat_wide[c];
+        cat_out[4 * c + 1] = pl.cat_row[c];
+        cat_out[4 * c + 2] = pl.cat_tab[c];
+        cat_out[4 * c + 3] = pl.cat_sink[c];
+    }
+    for (int t = 0; t < kCatMaxTiles; ++t) {
+        tile_out[4 * t + 0] = pl.tile_row[t];
+        tile_out[4 * t + 1] = pl.tile_code0[t];
+        tile_out[4 * t + 2] = pl.tile_nlev[t];
+        tile_out[4 * t + 3] = pl.tile_lev0[t];
+    }
+    return 0;
+}
+
 template <int ROUNDS, int NC, int NTILE>
 static int cat_launch_t(const CatArgs& a, const CatPlan& pl, cudaStream_t st) {
     auto kern = irls_cat_kernel<ROUNDS, NC, NTILE>;

@@ -211,6 +211,16 @@ int dlsa_onehot_expand_f64(const double *numeric, int n_num, const double *mean,
  *   dynamic shared memory (bytes), slots per CTA. */
 int dlsa_irls_tiled_schedule(int px, int fit_intercept, uint32_t *sched_out, int *info);
 
+/* Host-only diagnostic (no GPU work): the shared-memory layout the categorical pass (f-2) chooses for a shape.
+ *   info [12]: slices per partition, warps per CTA, 1 if warp pairs share one set of level tables, wide (scattered)
+ *   categoricals, scatter rounds, DMMA level tiles, bytes of one set of tables, bytes of one ring stage, bytes of a warp's
+ *   ring + row scratch, dynamic shared memory per CTA, cells of the pair histogram, padded levels.
+ *   cat_out [n_cat][4]: wide slot (-1 = narrow: on DMMA tiles), row of the per-row integer scratch, byte offset of the
+ *   categorical's level 0 inside the tables, byte offset of its sink.  tile_out [6][4]: scratch row, first code, live
+ *   levels (0 = unused tile), first level in level space. */
+int dlsa_irls_cat_plan(int K, int n_num, int n_cat, const int *n_levels_host, int64_t max_part_rows, int *info,
+                       int *cat_out, int *tile_out);
+
 /* f-3  describe(): count, mean, sample standard deviation, min, max of every column of X [n, ldx] in one streaming
  *   pass — the statistics the reference takes from Spark's data_sdf_i.describe() (projects/logistic_dlsa.py:279-283)
  *   and applies as (x - mean) / stddev in logistic_model (dlsa/models.py:99-101).

@@ -182,3 +182,65 @@ def test_tiled_schedule_covers_every_tile_exactly_once():
             assert np.array_equal(owner, lower), p                 # every lower-triangle tile exactly once, nothing else
             assert np.all(g_owner == 1), p                        # every column group's gradient has one owner
             assert max(per_warp_partials.values(), default=0) <= 1  # the body handles one partial block per warp
+
+
+def test_categorical_plan_gives_every_level_one_home():
+    """K1c's host-side layout (csrc/irls_cat.cu::cat_plan through the host-only dlsa_irls_cat_plan): every level of every
+    categorical lives either in exactly one DMMA tile slot or in its own 64-byte half row of a scatter table; no two of
+    those overlap, sinks included; the whole CTA fits 227 KB; pair-histogram cells = sum of (L+1)(L'+1)."""
+    import ctypes as C
+    from dlsa_b200 import _lib
+    rng = np.random.default_rng(4)
+    shapes = [(7, [11, 6, 7, 75, 75]), (0, [5]), (2, [3, 4]), (3, [8] * 8), (7, [20] * 8), (6, [40, 60, 90]),
+              (4, [16, 9, 16, 16]), (1, [1, 8, 2, 17]), (5, [1, 1, 30, 100]), (0, [192]), (7, [24] * 8)]
+    while len(shapes) < 150:
+        n_cat = int(rng.integers(1, 9))
+        lev = rng.integers(1, 60, size=n_cat)
+        while lev.sum() > 192:
+            lev[np.argmax(lev)] //= 2
+        shapes.append((int(rng.integers(0, 8)), [int(x) for x in lev]))
+    info, cat, tile = (C.c_int * 12)(), (C.c_int * 32)(), (C.c_int * 24)()
+    for n_num, lev in shapes:
+        n_cat = len(lev)
+        arr = (C.c_int * n_cat)(*lev)
+        for K, rows in ((120, 1_000_000), (3, 500), (1024, 60_000)):
+            assert _lib.lib.dlsa_irls_cat_plan(K, n_num, n_cat, arr, rows, info, cat, tile) == 0
+            S, warps, share, n_wide, rounds, ntiles, tab_bytes, stage, front, smem, npairs, Lpad = list(info)
+            assert 1 <= S <= 16 and 4 <= warps <= 16 and smem <= 227 * 1024 and Lpad >= sum(lev) and Lpad % 8 == 0
+            assert rounds == (n_wide + 1) // 2 and 0 <= ntiles <= 6
+            assert stage == 256 * n_num + 128 * n_cat + 256 and front >= 2 * stage + 2560 + 128 * n_cat
+            sets = (warps + 1) // 2 if share else warps
+            assert smem >= warps * front + sets * tab_bytes + 8 * (8 + Lpad)
+            want_pairs = sum((lev[a] + 1) * (lev[b] + 1) for a in range(n_cat) for b in range(a + 1, n_cat))
+            assert npairs == (want_pairs if n_cat > 1 else lev[0] + 1)
+            cats = np.array(list(cat)[:4 * n_cat]).reshape(n_cat, 4)
+            tiles = np.array(list(tile)).reshape(6, 4)
+            assert sorted(cats[:, 1]) == list(range(n_cat))                 # one scratch row per categorical
+            wide = [c for c in range(n_cat) if cats[c, 0] >= 0]
+            assert len(wide) == n_wide and sorted(cats[wide, 0]) == list(range(n_wide))
+            assert all(cats[c, 1] == cats[c, 0] for c in wide)               # wide slots come first in the scratch
+            used = np.zeros(max(tab_bytes, 1), dtype=np.int32)
+            for c in wide:
+                for code in range(lev[c]):
+                    used[cats[c, 2] + 128 * code: cats[c, 2] + 128 * code + 64] += 1
+                used[cats[c, 3]: cats[c, 3] + 64] += 1                       # its sink half row
+                assert cats[c, 2] % 64 == 0 and cats[c, 3] % 64 == 0
+                assert cats[c, 3] + 64 <= tab_bytes
+            assert used.max(initial=0) <= 1
+            # narrow categoricals: their levels are covered by tiles exactly once, level-space index consistent
+            lo = np.concatenate([[0], np.cumsum(lev)])
+            home = np.zeros(sum(lev), dtype=np.int32)
+            for t in range(6):
+                row, code0, nlev, lev0 = tiles[t]
+                if t >= ntiles:
+                    assert nlev == 0
+                    continue
+                c = int(np.flatnonzero(cats[:, 1] == row)[0])
+                assert cats[c, 0] < 0 and 1 <= nlev <= 8 and code0 % 8 == 0 and lev0 == lo[c] + code0
+                assert code0 + nlev <= lev[c] and lev[c] <= 16
+                home[lev0: lev0 + nlev] += 1
+            for c in range(n_cat):
+                assert (home[lo[c]: lo[c + 1]] == (0 if cats[c, 0] >= 0 else 1)).all()
+    bad = (C.c_int * 9)(*([3] * 9))
+    assert _lib.lib.dlsa_irls_cat_plan(4, 8, 2, bad, 100, info, cat, tile) != 0    # 8 numeric columns
+    assert _lib.lib.dlsa_irls_cat_plan(4, 2, 9, bad, 100, info, cat, tile) != 0    # 9 categorical columns

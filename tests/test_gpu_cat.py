@@ -248,3 +248,21 @@ def test_host_entry_for_the_compact_design_matches_the_device_entry(eng):
         assert float((f1.Sig_inv - f0.Sig_inv).norm() / f0.Sig_inv.norm()) < 1e-10
         assert (c1.beta_byOLS - c0.beta_byOLS).abs().max().item() < 1e-9
         assert p1.argmin_BIC == p0.argmin_BIC and torch.equal(p1.beta[p1.argmin_BIC] != 0, p0.beta[p0.argmin_BIC] != 0)
+
+
+def test_cat_pass_is_bitwise_reproducible_with_shared_tables(eng):
+    """Warp pairs take turns on one set of level tables in a fixed order (mbarrier hand-over): the sums must not depend on
+    timing.  Same pass five times on the airline shape, partitions of very different sizes: identical bits."""
+    from dlsa_b200 import synth
+    n = 3_000_000
+    num, codes, n_levels, y = synth.airline_shaped_device(n, 5, torch.device("cuda"))
+    sizes = np.array([1, 700_000, 33, 1_200_000, 4096, 1_095_870 - 4096 + 4096], dtype=np.int64)
+    sizes[-1] = n - sizes[:-1].sum()
+    off = torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]), device="cuda")
+    p = 1 + num.shape[1] + sum(n_levels)
+    beta = torch.randn(len(sizes), p, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(1)) * 0.2
+    g0, H0, ll0 = eng.irls_pass_cat(num, codes, n_levels, y, off, beta, fit_intercept=True)
+    g0, H0, ll0 = g0.clone(), H0.clone(), ll0.clone()
+    for _ in range(4):
+        g1, H1, ll1 = eng.irls_pass_cat(num, codes, n_levels, y, off, beta, fit_intercept=True)
+        assert torch.equal(g1, g0) and torch.equal(H1, H0) and torch.equal(ll1, ll0)
