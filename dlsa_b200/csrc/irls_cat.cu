@@ -46,6 +46,7 @@ constexpr int kCatMaxRowsPerCta = 1 << 20;
 constexpr int kCatMaxTiles = 6;     // 8-level DMMA tiles for the narrow categoricals
 constexpr int kTabPitch = 9;        // doubles per level in the PARTIALS: [unused | w z_1..7 | r]
 constexpr double kWScale = 17592186044416.0;  // 2^44
+constexpr int kIPitch = 40;                               // ints per row of the per-row integer scratch: 32 + 8 (see the tile loads)
 constexpr int kBPitch = 10;                                // doubles per row of b: r | w z_1..7 | 2 pad (bank spread, see the DMMA stage)
 
 struct CatArgs {
@@ -80,10 +81,10 @@ struct CatArgs {
     int share_tables;                    // 1: warps 2 i and 2 i + 1 take turns on one set of tables; 0: one set per warp
     int stage_bytes, front_bytes;        // one ring stage (numerics | codes | labels); ring + row scratch (tables follow)
     int ntiles;                          // DMMA level tiles in use
-    int tile_row[kCatMaxTiles];          // row of the per-row int scratch holding the categorical's codes
-    int tile_code0[kCatMaxTiles];        // first code (level within the categorical) of the tile
-    int tile_nlev[kCatMaxTiles];         // levels of the tile that exist (1..8)
-    int tile_lev0[kCatMaxTiles];         // level-space index of the tile's first level
+    // a tile is 8 SLOTS, each one (narrow categorical, code): the narrow levels are packed densely, categoricals mixed
+    short slot_row[kCatMaxTiles * 8];    // row of the per-row int scratch holding the slot's categorical's codes
+    short slot_code[kCatMaxTiles * 8];   // the code the slot stands for; -2 = unused slot
+    short slot_lev[kCatMaxTiles * 8];    // its level-space index
 };
 
 __device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, bool pred) {
@@ -125,7 +126,7 @@ __device__ __forceinline__ void pair_reds(const CatArgs& a, unsigned long long* 
     }
 }
 
-// ROUNDS = ceil(wide categoricals / 2) (0..4).  NC = categorical columns compiled into the row stage (4 or 8).
+// ROUNDS = ceil(wide categoricals / 2) (0..4).  NC = categorical columns compiled into the row stage (8).
 // NTILE = compiled DMMA level tiles (0, 2, 4, 6).
 template <int ROUNDS, int NC, int NTILE>
 __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const CatArgs a) {
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
     for (int q = 0; q < ROUNDS; ++q) {
         const int v = 2 * q + ((lane >> 3) & 1);
         sc_on[q] = v < a.n_wide && colj <= n_num;
-        sc_to[q] = irow_u32 + (uint32_t)(v < a.n_wide ? v : 0) * 128u;
+        sc_to[q] = irow_u32 + (uint32_t)(v < a.n_wide ? v : 0) * (kIPitch * 4u);
     }
     const uint32_t sc_b = bs_u32 + (uint32_t)half * (kBPitch * 8u) + 8u * colj;   // b[row 0 + half][j]
     // DMMA level tiles: lane (m = lane >> 2, k = lane & 3) holds one-hot[code code0 + m][row] of the A operand
@@ -251,8 +252,10 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
 #pragma unroll
     for (int t = 0; t < NTILE; ++t) {
         const bool on = t < a.ntiles;
-        tile_cmp[t] = on ? a.tile_code0[t] + (lane >> 2) : -2;   // codes are >= -1: -2 never matches
-        tile_to[t] = irow_u32 + (uint32_t)(on ? a.tile_row[t] : 0) * 128u + 8u * (lane & 3);
+        // slots of one tile may belong to different categoricals: with 40 ints per scratch row the 4 rows x up to 4
+        // categoricals a tile load touches fall into different banks (8 c + row)
+        tile_cmp[t] = on ? (int)a.slot_code[t * 8 + (lane >> 2)] : -2;   // codes are >= -1: -2 never matches
+        tile_to[t] = irow_u32 + (uint32_t)(on ? (int)a.slot_row[t * 8 + (lane >> 2)] : 0) * (kIPitch * 4u) + 8u * (lane & 3);
         td0[t] = 0.0;
         td1[t] = 0.0;
     }
@@ -291,18 +294,32 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
             }
         }
         int li[NC];   // 1 + level within the column; 0 = baseline level, no such column, or no such row
+        {
+            // all loads first (the level coefficients are gathered independently, then summed), stores afterwards: the
+            // compiler cannot move a shared load across a shared store on its own
+            double bv[NC];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            li[c] = 0;
-            if (c < n_cat) {
-                const int code = valid ? cs[lane * n_cat + c] : -1;
-                if (code >= 0) {
-                    li[c] = code + 1;
-                    eta += bl[a.cat_lo[c] + code];
+            for (int c = 0; c < NC; ++c) {
+                li[c] = 0;
+                bv[c] = 0.0;
+                if (c < n_cat) {
+                    const int code = valid ? cs[lane * n_cat + c] : -1;
+                    if (code >= 0) {
+                        li[c] = code + 1;
+                        bv[c] = bl[a.cat_lo[c] + code];
+                    }
                 }
-                // wide: byte offset of the level's half row in the warp's tables; narrow: the code itself
-                const int wide_to = code >= 0 ? a.cat_tab[c] + code * 128 : a.cat_sink[c];
-                irow[a.cat_row[c] * 32 + lane] = a.cat_wide[c] >= 0 ? wide_to : code;
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) eta += bv[c];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                if (c < n_cat) {
+                    // wide: byte offset of the level's half row in the warp's tables; narrow: the code itself
+                    const int code = li[c] - 1;
+                    const int wide_to = code >= 0 ? a.cat_tab[c] + code * 128 : a.cat_sink[c];
+                    irow[a.cat_row[c] * kIPitch + lane] = a.cat_wide[c] >= 0 ? wide_to : code;
+                }
             }
         }
         double w = 0.0, r = 0.0;
@@ -464,9 +481,8 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
                     srci = (a.cat_tab[c] + code * 128) / 8 + jj;
                     in_tab = true;
                 } else {
-                    for (int t = 0; t < a.ntiles; ++t)
-                        if (a.tile_lev0[t] <= level && level < a.tile_lev0[t] + a.tile_nlev[t])
-                            srci = 80 + t * 64 + (level - a.tile_lev0[t]) * 8 + jj;
+                    for (int sl = 0; sl < a.ntiles * 8; ++sl)
+                        if (a.slot_code[sl] >= 0 && a.slot_lev[sl] == level) srci = 80 + sl * 8 + jj;
                 }
             }
         }
@@ -578,7 +594,7 @@ struct CatPlan {
     // layout of the level work (see CatArgs)
     int n_wide, rounds, ntiles, tab_bytes, stage_bytes, front_bytes, share_tables;
     int cat_wide[kCatMaxC], cat_row[kCatMaxC], cat_tab[kCatMaxC], cat_sink[kCatMaxC];
-    int tile_row[kCatMaxTiles], tile_code0[kCatMaxTiles], tile_nlev[kCatMaxTiles], tile_lev0[kCatMaxTiles];
+    short slot_row[kCatMaxTiles * 8], slot_code[kCatMaxTiles * 8], slot_lev[kCatMaxTiles * 8];
 };
 
 int cat_sm_count() {
@@ -635,17 +651,17 @@ void cat_plan(int K, int n_num, int n_cat, const int* n_levels, int64_t max_part
         return v < 0 ? 0 : (v > kCatMaxTiles ? kCatMaxTiles : v);
     }();
     bool narrow[kCatMaxC] = {};
-    pl.ntiles = 0;
-    int n_narrow = 0;
+    int n_narrow = 0, n_slots = 0;
     for (;;) {
         int pick = -1;
         for (int c = 0; c < n_cat; ++c)
             if (!narrow[c] && n_levels[c] >= 1 && n_levels[c] <= 16 && (pick < 0 || n_levels[c] < n_levels[pick])) pick = c;
-        if (pick < 0 || pl.ntiles + (n_levels[pick] + 7) / 8 > tile_budget) break;
+        if (pick < 0 || n_slots + n_levels[pick] > 8 * tile_budget) break;
         narrow[pick] = true;
         ++n_narrow;
-        pl.ntiles += (n_levels[pick] + 7) / 8;
+        n_slots += n_levels[pick];
     }
+    pl.ntiles = (n_slots + 7) / 8;
     int wide[kCatMaxC];
     pl.n_wide = 0;
     for (int c = 0; c < n_cat; ++c)
@@ -667,24 +683,23 @@ void cat_plan(int K, int n_num, int n_cat, const int* n_levels, int64_t max_part
         pl.cat_sink[c] = pl.tab_bytes + (rows - 1) * 128 + which * 64;
     }
     if (pl.n_wide > 0) pl.tab_bytes += (n_levels[wide[2 * (pl.rounds - 1)]] + 1) * 128;
-    int t = 0, nrow = pl.n_wide;
+    int sl = 0, nrow = pl.n_wide;
     for (int c = 0; c < n_cat; ++c) {
         if (!narrow[c]) continue;
         pl.cat_row[c] = nrow;
-        for (int b = 0; b < n_levels[c]; b += 8, ++t) {
-            pl.tile_row[t] = nrow;
-            pl.tile_code0[t] = b;
-            pl.tile_nlev[t] = n_levels[c] - b < 8 ? n_levels[c] - b : 8;
-            pl.tile_lev0[t] = cat_lo[c] + b;
+        for (int code = 0; code < n_levels[c]; ++code, ++sl) {
+            pl.slot_row[sl] = (short)nrow;
+            pl.slot_code[sl] = (short)code;
+            pl.slot_lev[sl] = (short)(cat_lo[c] + code);
         }
         ++nrow;
     }
-    for (; t < kCatMaxTiles; ++t) pl.tile_row[t] = 0, pl.tile_code0[t] = 0, pl.tile_nlev[t] = 0, pl.tile_lev0[t] = 0;
+    for (; sl < kCatMaxTiles * 8; ++sl) pl.slot_row[sl] = 0, pl.slot_code[sl] = -2, pl.slot_lev[sl] = -1;
 
     // as many warps as shared memory allows (each owns a ring, a row scratch and its level tables)
     // (the ring + row scratch also stage the warp's small results at the end: 80 + 64 per tile doubles)
     pl.stage_bytes = 256 * n_num + 128 * n_cat + 256;
-    pl.front_bytes = kCatStages * pl.stage_bytes + 32 * kBPitch * 8 + 128 * n_cat;
+    pl.front_bytes = kCatStages * pl.stage_bytes + 32 * kBPitch * 8 + kIPitch * 4 * n_cat;
     if (pl.front_bytes < (80 + 64 * kCatMaxTiles) * 8) pl.front_bytes = (80 + 64 * kCatMaxTiles) * 8;
     const size_t fixed = (size_t)(8 + pl.Lpad) * 8 + 16 * (kCatMaxWarps / 2);
     const size_t budget = 227 * 1024;
@@ -722,7 +737,7 @@ size_t irls_cat_workspace_bytes(int K, int n_cat, const int* n_levels, int64_t m
 // Host-only: the layout cat_plan chooses, for tests.  info[12]: slices per partition, warps, tables shared by warp pairs,
 // wide categoricals, scatter rounds, DMMA tiles, table bytes (one set), ring stage bytes, front bytes, dynamic shared
 // memory, pair cells, padded levels.  cat_out [n_cat][4]: wide slot (-1 = narrow), scratch row, byte offset of level 0 in
-// the tables, byte offset of the sink.  tile_out [6][4]: scratch row, first code, live levels, first level (level space).
+// the tables, byte offset of the sink.  tile_out [48][3]: per tile slot its scratch row, code (-2 = unused), level (level space).
 int irls_cat_plan_info(int K, int n_num, int n_cat, const int* n_levels, int64_t max_part_rows, int* info, int* cat_out,
                        int* tile_out) {
     if (n_cat < 1 || n_cat > kCatMaxC || n_num < 0 || n_num > kCatMaxNum || K < 1) return -1;
@@ -737,11 +752,10 @@ int irls_cat_plan_info(int K, int n_num, int n_cat, const int* n_levels, int64_t
         cat_out[4 * c + 2] = pl.cat_tab[c];
         cat_out[4 * c + 3] = pl.cat_sink[c];
     }
-    for (int t = 0; t < kCatMaxTiles; ++t) {
-        tile_out[4 * t + 0] = pl.tile_row[t];
-        tile_out[4 * t + 1] = pl.tile_code0[t];
-        tile_out[4 * t + 2] = pl.tile_nlev[t];
-        tile_out[4 * t + 3] = pl.tile_lev0[t];
+    for (int sl = 0; sl < kCatMaxTiles * 8; ++sl) {
+        tile_out[3 * sl + 0] = pl.slot_row[sl];
+        tile_out[3 * sl + 1] = pl.slot_code[sl];
+        tile_out[3 * sl + 2] = pl.slot_lev[sl];
     }
     return 0;
 }
@@ -822,29 +836,20 @@ int irls_cat_launch(const double* numeric, int64_t ldn, int n_num, const double*
         a.cat_tab[c] = pl.cat_tab[c];
         a.cat_sink[c] = pl.cat_sink[c];
     }
-    for (int t = 0; t < kCatMaxTiles; ++t) {
-        a.tile_row[t] = pl.tile_row[t];
-        a.tile_code0[t] = pl.tile_code0[t];
-        a.tile_nlev[t] = pl.tile_nlev[t];
-        a.tile_lev0[t] = pl.tile_lev0[t];
+    for (int sl = 0; sl < kCatMaxTiles * 8; ++sl) {
+        a.slot_row[sl] = pl.slot_row[sl];
+        a.slot_code[sl] = pl.slot_code[sl];
+        a.slot_lev[sl] = pl.slot_lev[sl];
     }
     const int rounds = pl.rounds;              // 0..4
-    const int ntile = (pl.ntiles + 1) & ~1;    // 0, 2, 4, 6
-    const bool c4 = n_cat <= 4;
+    const int ntile = pl.ntiles == 5 ? 6 : pl.ntiles;    // 0, 1, 2, 3, 4, 6
     int rc = DLSA_E_UNSUPPORTED;
-#define DLSA_CAT_CASE4(R, T) \
-    if (c4 && rounds == R && ntile == T) rc = cat_launch_t<R, 4, T>(a, pl, st);
 #define DLSA_CAT_CASE8(R, T) \
-    if (!c4 && rounds == R && ntile == T) rc = cat_launch_t<R, 8, T>(a, pl, st);
-    DLSA_CAT_CASE4(0, 2) DLSA_CAT_CASE4(0, 4) DLSA_CAT_CASE4(0, 6)
-    DLSA_CAT_CASE4(1, 0) DLSA_CAT_CASE4(1, 2) DLSA_CAT_CASE4(1, 4) DLSA_CAT_CASE4(1, 6)
-    DLSA_CAT_CASE4(2, 0) DLSA_CAT_CASE4(2, 2) DLSA_CAT_CASE4(2, 4) DLSA_CAT_CASE4(2, 6)
-    DLSA_CAT_CASE8(0, 6)
-    DLSA_CAT_CASE8(1, 4) DLSA_CAT_CASE8(1, 6)
-    DLSA_CAT_CASE8(2, 2) DLSA_CAT_CASE8(2, 4) DLSA_CAT_CASE8(2, 6)
-    DLSA_CAT_CASE8(3, 0) DLSA_CAT_CASE8(3, 2) DLSA_CAT_CASE8(3, 4) DLSA_CAT_CASE8(3, 6)
-    DLSA_CAT_CASE8(4, 0) DLSA_CAT_CASE8(4, 2) DLSA_CAT_CASE8(4, 4) DLSA_CAT_CASE8(4, 6)
-#undef DLSA_CAT_CASE4
+    if (rounds == R && ntile == T) rc = cat_launch_t<R, 8, T>(a, pl, st);
+#define DLSA_CAT_ROW8(R) DLSA_CAT_CASE8(R, 0) DLSA_CAT_CASE8(R, 1) DLSA_CAT_CASE8(R, 2) DLSA_CAT_CASE8(R, 3) DLSA_CAT_CASE8(R, 4) DLSA_CAT_CASE8(R, 6)
+    DLSA_CAT_CASE8(0, 1) DLSA_CAT_CASE8(0, 2) DLSA_CAT_CASE8(0, 3) DLSA_CAT_CASE8(0, 4) DLSA_CAT_CASE8(0, 6)
+    DLSA_CAT_ROW8(1) DLSA_CAT_ROW8(2) DLSA_CAT_ROW8(3) DLSA_CAT_ROW8(4)
+#undef DLSA_CAT_ROW8
 #undef DLSA_CAT_CASE8
     DLSA_REQUIRE(rc != DLSA_E_UNSUPPORTED, DLSA_E_UNSUPPORTED, "categorical pass: no kernel for %d scatter rounds x %d tiles",
                  rounds, ntile);

@@ -216,8 +216,8 @@ int dlsa_irls_tiled_schedule(int px, int fit_intercept, uint32_t *sched_out, int
  *   categoricals, scatter rounds, DMMA level tiles, bytes of one set of tables, bytes of one ring stage, bytes of a warp's
  *   ring + row scratch, dynamic shared memory per CTA, cells of the pair histogram, padded levels.
  *   cat_out [n_cat][4]: wide slot (-1 = narrow: on DMMA tiles), row of the per-row integer scratch, byte offset of the
- *   categorical's level 0 inside the tables, byte offset of its sink.  tile_out [6][4]: scratch row, first code, live
- *   levels (0 = unused tile), first level in level space. */
+ *   categorical's level 0 inside the tables, byte offset of its sink.  tile_out [48][3]: for each of the 6 x 8 tile
+ *   slots the scratch row of its categorical, the code it stands for (-2 = unused slot) and its level (level space). */
 int dlsa_irls_cat_plan(int K, int n_num, int n_cat, const int *n_levels_host, int64_t max_part_rows, int *info,
                        int *cat_out, int *tile_out);
 

@@ -199,7 +199,7 @@ def test_categorical_plan_gives_every_level_one_home():
         while lev.sum() > 192:
             lev[np.argmax(lev)] //= 2
         shapes.append((int(rng.integers(0, 8)), [int(x) for x in lev]))
-    info, cat, tile = (C.c_int * 12)(), (C.c_int * 32)(), (C.c_int * 24)()
+    info, cat, tile = (C.c_int * 12)(), (C.c_int * 32)(), (C.c_int * 144)()
     for n_num, lev in shapes:
         n_cat = len(lev)
         arr = (C.c_int * n_cat)(*lev)
@@ -208,13 +208,13 @@ def test_categorical_plan_gives_every_level_one_home():
             S, warps, share, n_wide, rounds, ntiles, tab_bytes, stage, front, smem, npairs, Lpad = list(info)
             assert 1 <= S <= 16 and 4 <= warps <= 16 and smem <= 227 * 1024 and Lpad >= sum(lev) and Lpad % 8 == 0
             assert rounds == (n_wide + 1) // 2 and 0 <= ntiles <= 6
-            assert stage == 256 * n_num + 128 * n_cat + 256 and front >= 2 * stage + 2560 + 128 * n_cat
+            assert stage == 256 * n_num + 128 * n_cat + 256 and front >= 2 * stage + 2560 + 160 * n_cat
             sets = (warps + 1) // 2 if share else warps
             assert smem >= warps * front + sets * tab_bytes + 8 * (8 + Lpad)
             want_pairs = sum((lev[a] + 1) * (lev[b] + 1) for a in range(n_cat) for b in range(a + 1, n_cat))
             assert npairs == (want_pairs if n_cat > 1 else lev[0] + 1)
             cats = np.array(list(cat)[:4 * n_cat]).reshape(n_cat, 4)
-            tiles = np.array(list(tile)).reshape(6, 4)
+            slots = np.array(list(tile)).reshape(48, 3)
             assert sorted(cats[:, 1]) == list(range(n_cat))                 # one scratch row per categorical
             wide = [c for c in range(n_cat) if cats[c, 0] >= 0]
             assert len(wide) == n_wide and sorted(cats[wide, 0]) == list(range(n_wide))
@@ -227,18 +227,21 @@ def test_categorical_plan_gives_every_level_one_home():
                 assert cats[c, 2] % 64 == 0 and cats[c, 3] % 64 == 0
                 assert cats[c, 3] + 64 <= tab_bytes
             assert used.max(initial=0) <= 1
-            # narrow categoricals: their levels are covered by tiles exactly once, level-space index consistent
+            # narrow categoricals: every level has exactly one tile slot, slots are packed densely (categoricals mixed)
             lo = np.concatenate([[0], np.cumsum(lev)])
             home = np.zeros(sum(lev), dtype=np.int32)
-            for t in range(6):
-                row, code0, nlev, lev0 = tiles[t]
-                if t >= ntiles:
-                    assert nlev == 0
+            n_used = 0
+            for sl in range(48):
+                row, code, level = slots[sl]
+                if code < 0:
+                    assert code == -2 and sl >= n_used
                     continue
+                assert sl == n_used and sl < 8 * ntiles
+                n_used += 1
                 c = int(np.flatnonzero(cats[:, 1] == row)[0])
-                assert cats[c, 0] < 0 and 1 <= nlev <= 8 and code0 % 8 == 0 and lev0 == lo[c] + code0
-                assert code0 + nlev <= lev[c] and lev[c] <= 16
-                home[lev0: lev0 + nlev] += 1
+                assert cats[c, 0] < 0 and 0 <= code < lev[c] <= 16 and level == lo[c] + code
+                home[level] += 1
+            assert ntiles == (n_used + 7) // 8
             for c in range(n_cat):
                 assert (home[lo[c]: lo[c + 1]] == (0 if cats[c, 0] >= 0 else 1)).all()
     bad = (C.c_int * 9)(*([3] * 9))
