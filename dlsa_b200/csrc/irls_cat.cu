@@ -152,7 +152,9 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
     unsigned char* tab = tab_all + (size_t)(warp >> tshift) * a.tab_bytes;
     double* bz = reinterpret_cast<double*>(tab_all + (size_t)npair * a.tab_bytes);
     double* bl = bz + 8;
-    const uint32_t turn = smem_u32(bl + a.Lpad) + 16u * (warp >> 1);   // [0]: the even warp is done, [1]: the odd warp is done
+    double* mean_s = bl + a.Lpad;   // [8] column means, [8] reciprocal standard deviations (standardisation on load)
+    double* rsd_s = mean_s + 8;
+    const uint32_t turn = smem_u32(rsd_s + 8) + 16u * (warp >> 1);   // [0]: the even warp is done, [1]: the odd warp is done
     const bool paired = a.share_tables && (warp | 1) < nwarps;         // the last warp of an odd count has its tables alone
 
     // coefficients in internal order: [intercept | numerics (7) | levels]; zero this warp's tables
@@ -165,6 +167,11 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
             else if (i < 8) v = (i - 1 < n_num) ? bk[a.fit_intercept + i - 1] : 0.0;
             else if (i - 8 < a.Ltot) v = bk[a.fit_intercept + n_num + (i - 8)];
             bz[i] = v;
+        }
+        if (threadIdx.x < 8) {
+            const bool on = a.mean != nullptr && (int)threadIdx.x < n_num;
+            mean_s[threadIdx.x] = on ? a.mean[threadIdx.x] : 0.0;
+            rsd_s[threadIdx.x] = on ? 1.0 / a.sd[threadIdx.x] : 1.0;
         }
         double* t = reinterpret_cast<double*>(tab_all);
         for (int i = threadIdx.x; i < npair * (a.tab_bytes / 8); i += blockDim.x) t[i] = 0.0;
@@ -280,19 +287,25 @@ __global__ void __launch_bounds__(kCatMaxWarps * 32, 1) irls_cat_kernel(const Ca
         const bool valid = lane < nv;
         double eta = bz[0];
         double z[kCatMaxNum];
+        if (a.mean != nullptr) {   // one warp-uniform branch around the whole loop: inside it ptxas predicates the extra
+                                   // FP64 instructions, and a predicated-off FP64 instruction still takes its pipe slot
 #pragma unroll
-        for (int j = 0; j < kCatMaxNum; ++j) {
-            z[j] = 0.0;
-            if (j < n_num) {
-                double v = zs[lane * n_num + j];
-                if (a.mean != nullptr) {  // dlsa/models.py:99-101, same expression as dlsa_onehot_expand_f64
-                    v = (v - a.mean[j]) / a.sd[j];
+            for (int j = 0; j < kCatMaxNum; ++j) {
+                z[j] = 0.0;
+                if (j < n_num) {
+                    // (x - mean) / std of dlsa/models.py:99-101 with the reciprocal taken once per CTA (<= 1 ulp from the
+                    // division; 7 FP64 divisions per row and pass otherwise)
+                    const double v = (zs[lane * n_num + j] - mean_s[j]) * rsd_s[j];
                     zs[lane * n_num + j] = v;
+                    z[j] = v;
                 }
-                z[j] = v;
-                eta = fma(v, bz[1 + j], eta);
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kCatMaxNum; ++j) z[j] = (j < n_num) ? zs[lane * n_num + j] : 0.0;
         }
+#pragma unroll
+        for (int j = 0; j < kCatMaxNum; ++j) eta = fma(z[j], bz[1 + j], eta);   // bz is 0 beyond n_num
         int li[NC];   // 1 + level within the column; 0 = baseline level, no such column, or no such row
         {
             // all loads first (the level coefficients are gathered independently, then summed), stores afterwards: the
@@ -701,7 +714,7 @@ void cat_plan(int K, int n_num, int n_cat, const int* n_levels, int64_t max_part
     pl.stage_bytes = 256 * n_num + 128 * n_cat + 256;
     pl.front_bytes = kCatStages * pl.stage_bytes + 32 * kBPitch * 8 + kIPitch * 4 * n_cat;
     if (pl.front_bytes < (80 + 64 * kCatMaxTiles) * 8) pl.front_bytes = (80 + 64 * kCatMaxTiles) * 8;
-    const size_t fixed = (size_t)(8 + pl.Lpad) * 8 + 16 * (kCatMaxWarps / 2);
+    const size_t fixed = (size_t)(8 + pl.Lpad + 16) * 8 + 16 * (kCatMaxWarps / 2);   // beta | mean, 1/std | mbarriers
     const size_t budget = 227 * 1024;
     auto smem_for = [&](int w, int share) {
         return (size_t)w * pl.front_bytes + (size_t)(share ? (w + 1) / 2 : w) * pl.tab_bytes + fixed;
