@@ -678,17 +678,23 @@ static TiledCfg tiled_cfg(int px, int p) {
 }
 
 static int tiled_slices(int K, int TG, int CH, int64_t max_part_rows) {
+    // Slices per partition: S > 1 fills the SMs when K * TG CTAs do not, at a price per CTA — ring fill, accumulator
+    // flush, and a partial H that a second kernel has to sum.  Model: time ~ waves(S) x (chunks per CTA + overhead), the
+    // overhead taken as 8 chunks (r02 ncu at p = 500, 31-chunk CTAs: 10 % of the samples in prologue + epilogue, plus
+    // 10 GB of partials written and read back per pass; the old rule — best wave fill, 1 % hysteresis — took S = 5 there
+    // for 98.8 -> 99.9 % fill).
     const int64_t chunks = (max_part_rows + CH - 1) / CH;
     int64_t s_cap = chunks / 8;
     if (s_cap < 1) s_cap = 1;
     if (s_cap > 32) s_cap = 32;
     const int64_t sms = 148;
-    double best_eff = -1.0;
+    const double ovh = 8.0;
+    double best_cost = 0.0;
     int best_s = 1;
     for (int64_t s = 1; s <= s_cap; s++) {
         const int64_t u = (int64_t)K * TG * s;
-        const double eff = (double)u / (double)(sms * ((u + sms - 1) / sms));
-        if (eff > best_eff + 0.01) { best_eff = eff; best_s = (int)s; }  // a larger S must buy > 1 % to be taken
+        const double cost = (double)((u + sms - 1) / sms) * ((double)((chunks + s - 1) / s) + ovh);
+        if (s == 1 || cost < 0.98 * best_cost) { best_cost = cost; best_s = (int)s; }  // a larger S must buy > 2 %
     }
     return best_s;
 }
