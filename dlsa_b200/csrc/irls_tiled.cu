@@ -76,6 +76,11 @@ struct TiledArgs {
     uint32_t sched[kTMaxTG * kTMma * kTNBW];
 };
 
+#ifndef DLSA_TILED_KS_UNROLL
+#define DLSA_TILED_KS_UNROLL 1   // k-steps of a 16-row half chunk unrolled in the MMA bodies.  Rolled (1) beats 2 and 4 on every shape (r02 same-run A/B: c4 24.9 / 23.0 / 21.6 ms for 4 / 2 / 1; c5 26.2 / 25.2 / 24.7): the 12 MMA warps run different bodies and the unrolled ones do not fit the instruction caches (no_instruction stalls 0.3-1.1 per issue)
+#endif
+constexpr int kTKsUnroll = DLSA_TILED_KS_UNROLL;
+
 template <int N>
 __device__ __forceinline__ void t_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -96,7 +101,7 @@ __device__ __forceinline__ void tiled_chunk_body(const double* __restrict__ T, c
     constexpr int N0 = pat_n0(PAT), N1 = pat_n1(PAT);
 #pragma unroll 1
     for (int hb = 0; hb < NH; hb++, T += (size_t)16 * Sd, ws += 16, rs += 16)
-#pragma unroll
+#pragma unroll(kTKsUnroll)
     for (int ks = 0; ks < 4; ks++) {
         const double wv = LOGIT ? ws[4 * ks] : 1.0;
         const double* Tr = T + (size_t)(4 * ks) * Sd;  // row 4ks + q
