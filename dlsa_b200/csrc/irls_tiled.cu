@@ -71,6 +71,8 @@ struct TiledArgs {
     const double* pre_ll;
     int K, px, p, icpt, S, Sd, aligned, want_ll, NT, TG, stages, copy_cols;
     int poisson;  // GLM instantiation only: 0 = logistic link, 1 = log link (DLSA_FAMILY_POISSON)
+    int ycol;     // linear family: y rides the Gram as column `ycol` (= p) of the staged rows, so g = X'y is row p of the
+                  // augmented Gram and no warp issues gradient DFMAs; -1 = off (GLM families, p = 512)
     // block of MMA warp w, slot b of sibling tg: bits 0-7 valid-tile mask (bit 4*ii+jj), 8-15 row pair m, 16-23 column
     // group J, 24 g-owner flag, 25-27 partial pattern; 0 = empty slot.  Full blocks first, the partial one last.
     uint32_t sched[kTMaxTG * kTMma * kTNBW];
@@ -130,11 +132,13 @@ __device__ __forceinline__ void tiled_chunk_body(const double* __restrict__ T, c
                 if (jj < N0) dmma884(C[b][0][jj][0], C[b][0][jj][1], a0, f[jj]);
                 if (jj < N1) dmma884(C[b][1][jj][0], C[b][1][jj][1], a1, f[jj]);
             }
+#ifndef DLSA_TILED_EXPERIMENT_NO_G   // timing experiment only (wrong gradient): what the owner warps' DFMAs cost
             if (HASG && has_g) {  // has_g: run-time owner flag (GLM instantiation, see the dispatch below)
                 const double rv = rs[4 * ks];
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) gacc[jj] = fma(rv, f[jj], gacc[jj]);
             }
+#endif
         }
     }
 }
@@ -320,8 +324,9 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
                 ws_all[st * kTCH + row] = rowvalid ? wv : 0.0;
                 rs_all[st * kTCH + row] = rowvalid ? rv : 0.0;
                 if (fix_pad) tiles[(size_t)st * stage_doubles + (size_t)row * Sd + px] = pad_val;
+                if (!LOGIT && a.ycol >= 0) tiles[(size_t)st * stage_doubles + (size_t)row * Sd + a.ycol] = rowvalid ? yv : 0.0;
             }
-            if (fix_pad) fence_proxy_async();  // generic-proxy writes into a stage the TMA will overwrite later
+            if (fix_pad || (!LOGIT && a.ycol >= 0)) fence_proxy_async();  // generic-proxy writes into a stage the TMA will overwrite later
             __syncwarp();
             if (lane == 0) t_mbar_arrive(smem_u32(&bars[st * 4 + 1]));
             st += kTLink;
@@ -410,7 +415,9 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
                             const int r_ = 8 * i + a8, c_ = 8 * j + 2 * q + h;
-                            if (r_ < p && c_ < p && (i != j || c_ <= r_)) {
+                            if (!LOGIT && r_ == a.ycol && c_ < p) {   // row p of the augmented Gram: g = X'y
+                                a.outg[(size_t)item * p + (a.icpt ? (c_ == px ? 0 : c_ + 1) : c_)] = C[b][ii][jj][h];
+                            } else if (r_ < p && c_ < p && (i != j || c_ <= r_)) {
                                 const int ro = a.icpt ? (r_ == px ? 0 : r_ + 1) : r_;
                                 const int co = a.icpt ? (c_ == px ? 0 : c_ + 1) : c_;
                                 oH[(size_t)ro * p + co] = C[b][ii][jj][h];
@@ -564,9 +571,10 @@ static int pattern_of(uint32_t mask) {
     return -1;
 }
 
-static TiledCfg tiled_cfg(int px, int p) {
+// ycol: the linear family's Gram is that of [X | y] (p + 1 columns) and nobody owns g; GLM: p columns, g owned per column group
+static TiledCfg tiled_cfg(int px, int p, bool ycol = false) {
     TiledCfg c;
-    c.NT = (p + 7) / 8;
+    c.NT = (p + (ycol ? 1 : 0) + 7) / 8;
     const int MR = (c.NT + 1) / 2;
     struct Blk { int m, J; uint32_t mask; bool g; };
     std::vector<Blk> full, part;
@@ -582,7 +590,7 @@ static TiledCfg tiled_cfg(int px, int p) {
             // g of tile columns 4J..4J+3 belongs to the lowest diagonal block of that column group
             const int mg = (2 * J + 1 < MR) ? 2 * J + 1 : MR - 1;
             if (mask == 0xffu) full.push_back({m, J, mask, false});
-            else part.push_back({m, J, mask, m == mg});
+            else part.push_back({m, J, mask, !ycol && m == mg});
         }
     // (Tried and measured slower: one body per BLOCK instead of per (full-block count, partial shape), blocks run one
     // after the other, so that any mix of shapes can share a warp and the deal can equalise tiles per warp (p=100: 7..8
@@ -656,7 +664,7 @@ static TiledCfg tiled_cfg(int px, int p) {
         if (wpart[w].mask) c.sched[(size_t)w * kTNBW + slot++] = enc(wpart[w]);
     }
     int cols = 8 * 4 * ((c.NT + 3) / 4);   // every fragment column a block can touch exists in shared memory
-    if (cols < px + 1) cols = px + 1;
+    if (cols < p + 1) cols = p + 1;
     c.Sd = cols;
     while (c.Sd % 16 != 4) c.Sd++;
     const size_t fixed = ((size_t)c.Sd + 4) * 8 + 256;
@@ -724,6 +732,8 @@ int irls_tiled_schedule_info(int px, int icpt, uint32_t* sched_out, int* info) {
     return 0;
 }
 
+static bool tiled_linear_ycol(int p) { return p + 1 <= kTiledMaxP; }
+
 static bool tiled_use_pre(const TiledCfg& c, int K, int64_t max_part_rows) {
     return c.pre && 3.0 * sizeof(double) * (double)K * (double)max_part_rows <= 16.0 * 1024 * 1024 * 1024;
 }
@@ -732,7 +742,12 @@ static bool tiled_use_pre(const TiledCfg& c, int K, int64_t max_part_rows) {
 size_t irls_tiled_workspace_bytes(int K, int p, int64_t max_part_rows) {
     if (p > kTiledMaxP) return 0;
     TiledCfg c = tiled_cfg(p, p);
-    const int S = tiled_slices(K, c.TG, c.CH, max_part_rows);
+    int S = tiled_slices(K, c.TG, c.CH, max_part_rows);
+    if (tiled_linear_ycol(p)) {   // the family is not known here: room for whichever layout slices more
+        TiledCfg cl = tiled_cfg(p, p, true);
+        const int Sl = tiled_slices(K, cl.TG, cl.CH, max_part_rows);
+        if (Sl > S) S = Sl;
+    }
     size_t need = tiled_slice_bytes(K, S, p);
     if (tiled_use_pre(c, K, max_part_rows)) need += 3 * (size_t)K * (size_t)max_part_rows * sizeof(double);
     return need;
@@ -743,7 +758,8 @@ int irls_tiled_launch(const double* X, int64_t ldx, const double* y, const int64
                       int64_t max_part_rows, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const int p = px + (icpt ? 1 : 0);
     DLSA_REQUIRE(p <= kTiledMaxP, DLSA_E_UNSUPPORTED, "irls pass: p=%d > %d not supported", p, kTiledMaxP);
-    TiledCfg c = tiled_cfg(px, p);
+    const bool ycol = family == DLSA_FAMILY_LINEAR && tiled_linear_ycol(p);
+    TiledCfg c = tiled_cfg(px, p, ycol);
     DLSA_REQUIRE(c.TG <= kTMaxTG && c.stages >= 3, DLSA_E_UNSUPPORTED, "irls pass: p=%d does not fit (TG=%d, stages=%d)",
                  p, c.TG, c.stages);
     const int S = tiled_slices(K, c.TG, c.CH, max_part_rows);
@@ -758,6 +774,7 @@ int irls_tiled_launch(const double* X, int64_t ldx, const double* y, const int64
     double *pH = nullptr, *pg = nullptr, *pll = nullptr;
     const bool glm = family != DLSA_FAMILY_LINEAR;  // logistic or Poisson: the GLM instantiation, link chosen at run time
     a.poisson = family == DLSA_FAMILY_POISSON ? 1 : 0;
+    a.ycol = ycol ? p : -1;
     const bool pre = glm && tiled_use_pre(c, K, max_part_rows);
     const size_t slice_bytes = tiled_slice_bytes(K, S, p);
     const size_t need = slice_bytes + (pre ? 3 * (size_t)K * (size_t)max_part_rows * sizeof(double) : 0);
