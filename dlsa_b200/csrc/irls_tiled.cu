@@ -107,6 +107,9 @@ __device__ __forceinline__ void tiled_chunk_body(const double* __restrict__ T, c
     for (int ks = 0; ks < 4; ks++) {
         const double wv = LOGIT ? ws[4 * ks] : 1.0;
         const double* Tr = T + (size_t)(4 * ks) * Sd;  // row 4ks + q
+        // (Timing experiment, r02: one scaled A fragment pair shared by all full blocks of the warp — the upper bound of a
+        // schedule that deals row strips — is SLOWER for the GLM bodies, p=500 24.75 -> 25.63 ms, and gains 3 % for the
+        // linear ones: the w-scaling DMULs are not what the GLM bodies wait for.)
 #pragma unroll
         for (int b = 0; b < NF; b++) {
             double a0 = Tr[offA[b]], a1 = Tr[offA[b] + 8];
@@ -132,13 +135,11 @@ __device__ __forceinline__ void tiled_chunk_body(const double* __restrict__ T, c
                 if (jj < N0) dmma884(C[b][0][jj][0], C[b][0][jj][1], a0, f[jj]);
                 if (jj < N1) dmma884(C[b][1][jj][0], C[b][1][jj][1], a1, f[jj]);
             }
-#ifndef DLSA_TILED_EXPERIMENT_NO_G   // timing experiment only (wrong gradient): what the owner warps' DFMAs cost
             if (HASG && has_g) {  // has_g: run-time owner flag (GLM instantiation, see the dispatch below)
                 const double rv = rs[4 * ks];
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) gacc[jj] = fma(rv, f[jj], gacc[jj]);
             }
-#endif
         }
     }
 }
@@ -370,8 +371,9 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
         // keeps the instruction footprint of the 12 MMA warps inside the 32 KB instruction cache.
         // Linear family: owners and non-owners run different bodies (same-run A/B, 5e7 rows x p=100: 23.35 -> 21.70 ms).
         // GLM family: every warp runs the owner body with the run-time flag — the compiled-out variant measured SLOWER
-        // there (p=100 fused link 25.4 -> 27.3 ms, p=500 28.3 -> 29.2 ms; only p=182 gained, 23.6 -> 22.1), so it keeps
-        // the round-1 code; profiles/r02_k1_tiled_ab.md.
+        // there (p=100 fused link 25.4 -> 27.3 ms, p=500 28.3 -> 29.2 ms; only p=182 gained, 23.6 -> 22.1), and again with the
+        // rolled k-step loop (p=182 22.6 -> 23.1, p=100 25.5 -> 25.8, p=500 unchanged), so it keeps the round-1 code;
+        // profiles/r02_k1_tiled_ab.md.
         const int path = pat * 8 + ((LOGIT || has_g) ? 4 : 0) + nfull;
         int st = 0;
         uint32_t par = 0;
