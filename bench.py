@@ -692,7 +692,7 @@ def measure_e2e(ctx, wl, steps, pinned=True):
         return {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
 
 
-def short_config_line(ctx, cfg, f64_peak, f64_src, steps=1, warmup=1):
+def short_config_line(ctx, cfg, f64_peak, f64_src, steps=2, warmup=2):
     """other_configs entry: a short measurement of another BASELINE configuration on the same box."""
     try:
         wl = make_workload(ctx, cfg)
