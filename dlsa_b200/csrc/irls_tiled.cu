@@ -324,7 +324,9 @@ __global__ void __launch_bounds__(kTThreads, 1) irls_tiled_kernel(const __grid_c
             if (act) {
                 ws_all[st * kTCH + row] = rowvalid ? wv : 0.0;
                 rs_all[st * kTCH + row] = rowvalid ? rv : 0.0;
-                if (fix_pad) tiles[(size_t)st * stage_doubles + (size_t)row * Sd + px] = pad_val;
+                // (linear family: the A fragments are not scaled by w, so an intercept 1.0 in a row past `valid` would be
+                // counted — found by tests/test_gpu_parity.py::test_linear_pass_y_column_edge_widths, odd px + intercept)
+                if (fix_pad) tiles[(size_t)st * stage_doubles + (size_t)row * Sd + px] = (LOGIT || rowvalid) ? pad_val : 0.0;
                 if (!LOGIT && a.ycol >= 0) tiles[(size_t)st * stage_doubles + (size_t)row * Sd + a.ycol] = rowvalid ? yv : 0.0;
             }
             if (fix_pad || (!LOGIT && a.ycol >= 0)) fence_proxy_async();  // generic-proxy writes into a stage the TMA will overwrite later

@@ -406,6 +406,38 @@ def test_linear_p300_sixteen_row_chunks_with_ragged_tails(eng):
         assert abs(yh[k] - yk @ yk) <= 1e-9 * (yk @ yk)
 
 
+@pytest.mark.parametrize("px,icpt", [(9, True), (50, True), (55, True), (56, False), (57, False), (63, True), (64, False), (96, False), (103, True), (104, False),
+                                     (181, True), (511, False), (511, True), (512, False)])
+def test_linear_pass_y_column_edge_widths(eng, px, icpt):
+    """Linear family: y rides the Gram as column p of the staged rows (g = row p of the Gram of [X y]).  Widths where
+    that column opens a new tile row (p % 8 == 0), sits in the padding of the last one, collides with the column an odd
+    px drags along, follows the intercept column, is the last one that fits (p + 1 = 512) — and p = 512, where the kernel
+    falls back to the gradient-owner bodies."""
+    rng = np.random.default_rng(px * 2 + icpt)
+    sizes = [300, 1, 33, 257]
+    n = int(np.sum(sizes))
+    X = rng.standard_normal((n, px))
+    y = X[:, :5] @ np.arange(1.0, 6.0) + 0.5 + rng.standard_normal(n)
+    off = ragged_offsets(sizes)
+    Xd = dev(X)
+    variants = [Xd]
+    if px % 2:   # even row pitch: rows go by one bulk copy each and drag the (garbage) padding column along
+        Xpad = torch.full((n, px + 1), 7.25, dtype=torch.float64, device="cuda")
+        Xpad[:, :px] = Xd
+        variants.append(Xpad[:, :px])
+    for Xv in variants:
+        g, H, yty = eng.irls_pass(Xv, dev(y), dev(off, torch.int64), None, icpt, 1, want_loglik=True)
+        Hh, gh, yh = H.cpu().numpy(), g.cpu().numpy(), yty.cpu().numpy()
+        for k in range(len(sizes)):
+            Xk, yk = X[off[k]:off[k + 1]], y[off[k]:off[k + 1]]
+            if icpt:
+                Xk = np.hstack([np.ones((Xk.shape[0], 1)), Xk])
+            assert relfro(Hh[k], Xk.T @ Xk) < 1e-12
+            assert np.max(np.abs(gh[k] - Xk.T @ yk)) < 1e-9 * max(1.0, np.max(np.abs(Xk.T @ yk)))
+            assert abs(yh[k] - yk @ yk) <= 1e-9 * (yk @ yk)
+            assert np.array_equal(Hh[k], Hh[k].T)
+
+
 def test_glm_pass_on_a_window_of_the_offsets(eng):
     """A window part_offsets[lo:hi+1] of a longer offsets array with the SHARED X (what parallel.shard_partitions hands
     out): the streaming link kernel's w / r buffers are indexed relative to the window's first row."""
