@@ -63,6 +63,32 @@ def test_irls_pass_matches_oracle(eng, px, icpt):
         assert np.array_equal(H[k], H[k].T)  # exactly symmetric by construction
 
 
+@pytest.mark.parametrize("px,icpt", [(57, False), (64, True), (65, False), (100, True), (128, False), (169, False),
+                                     (170, True), (200, False), (256, False), (400, True), (511, True), (512, False)])
+def test_irls_pass_tiled_widths_match_oracle(eng, px, icpt):
+    """The CTA-tiled pass over the widths where its geometry changes (sibling CTAs from p ~ 170, 16-row chunks, streaming
+    link kernel, ragged last tile row, p = 512), partitions shorter than a chunk, of one row, empty, and with tail chunks."""
+    rng = np.random.default_rng(px * 7 + icpt)
+    sizes = [0, 1, 15, 33, 700, 64]
+    off = ragged_offsets(sizes)
+    n = int(off[-1])
+    p = px + int(icpt)
+    X = rng.random((n, px)) - 0.5
+    y = (rng.random(n) < 0.4).astype(np.float64)
+    beta = rng.standard_normal((len(sizes), p)) * (2.0 / np.sqrt(p))
+    g, H, ll = eng.irls_pass(dev(X), dev(y), dev(off, torch.int64), dev(beta), fit_intercept=icpt)
+    g, H, ll = g.cpu().numpy(), H.cpu().numpy(), ll.cpu().numpy()
+    for k, nk in enumerate(sizes):
+        Xk = X[off[k]:off[k + 1]]
+        if icpt:
+            Xk = np.concatenate([np.ones((nk, 1)), Xk], axis=1)
+        g0, H0, ll0 = onp.irls_pass(Xk, y[off[k]:off[k + 1]], beta[k])
+        assert np.allclose(g[k], g0, rtol=1e-10, atol=1e-11), (k, nk)
+        assert np.allclose(H[k], H0, rtol=1e-10, atol=1e-12), (k, nk)
+        assert abs(ll[k] - ll0) <= 1e-11 * max(1.0, abs(ll0))
+        assert np.array_equal(H[k], H[k].T)
+
+
 def test_irls_pass_saturated_eta_and_slices(eng):
     """eta = +-40 rows (weights underflow towards 0) and a few big partitions (sliced across CTAs)."""
     rng = np.random.default_rng(5)
