@@ -75,6 +75,9 @@ constexpr int kNB = 32;
 constexpr int kDPitch = 33;
 constexpr int kPPitch = 36;  // == 4 (mod 16) doubles: 16-byte aligned rows, (row a8, column pair q) stores spread over the banks
 
+// The right-hand side rides along as ROW p of the matrix: its "factor row" L[p][0:p] is z = L^-1 b, so the forward
+// substitution (16 serial block steps with every other warp waiting, ~10 % of the kernel in the r02 ncu capture) is part
+// of the panel GEMMs.  Rows of the panel therefore run to p inclusive; L has p + 1 rows.
 __device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, double* L, int ld, int p, double* x,
                                                  double* sm, int* ok_s) {
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
@@ -85,10 +88,10 @@ __device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, d
     double* P = W + kNB * kPPitch;
     if (tid == 0) *ok_s = 1;
     __syncthreads();
-    const int pcap = (p + 31) >> 5;   // 32-row blocks P has room for
+    const int pcap = (p + 32) >> 5;   // 32-row blocks P has room for (rows 0..p)
     for (int kb = 0; kb < p; kb += kNB) {
         const int nb = (p - kb < kNB) ? (p - kb) : kNB;
-        const int rows_total = p - kb;                 // rows of the panel, the diagonal block first
+        const int rows_total = p + 1 - kb;             // rows of the panel, the diagonal block first, the rhs row last
         const int nrb = (rows_total + 31) >> 5;
         // (1) panel update on DMMA: 32 rows x 32 columns per warp and turn, k over the finished columns 0..kb-1.  Late panels
         // have few row blocks and long k loops: the k range is then SPLIT over the idle warps (nsp parts per block), the
@@ -112,7 +115,7 @@ __device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, d
 #pragma unroll
             for (int t = 0; t < 4; t++) {
                 const int ra = r0 + 8 * t + a8, rb = kb + 8 * t + a8;
-                aok[t] = ra < p;
+                aok[t] = ra <= p;
                 bok[t] = rb < p;
                 ao[t] = (aok[t] ? ra : p - 1) * ld + 2 * q;
                 bo[t] = (bok[t] ? rb : p - 1) * ld + 2 * q;
@@ -148,9 +151,10 @@ __device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, d
                     double v0 = c0[ti][tj], v1 = c1[ti][tj];
                     if (nsp == 1) {
                         v0 = 0.0, v1 = 0.0;
-                        if (r < p) {   // the entries of A are read here, once; L only ever holds finished columns
-                            if (c < kb + nb && c <= r) v0 = A[(size_t)r * p + c] - c0[ti][tj];
-                            if (c + 1 < kb + nb && c + 1 <= r) v1 = A[(size_t)r * p + c + 1] - c1[ti][tj];
+                        if (r <= p) {   // the entries of A (row p: of b) are read here, once; L only ever holds finished columns
+                            const double* Ar = r < p ? A + (size_t)r * p : x;
+                            if (c < kb + nb && c <= r) v0 = Ar[c] - c0[ti][tj];
+                            if (c + 1 < kb + nb && c + 1 <= r) v1 = Ar[c + 1] - c1[ti][tj];
                         }
                     }
                     *reinterpret_cast<double2*>(P + (size_t)(32 * (sp * nrb + b) + 8 * ti + a8) * kPPitch + 8 * tj + 2 * q) =
@@ -170,9 +174,10 @@ __device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, d
                     s1 += v.y;
                 }
                 double v0 = 0.0, v1 = 0.0;
-                if (r < p) {
-                    if (c < kb + nb && c <= r) v0 = A[(size_t)r * p + c] - s0;
-                    if (c + 1 < kb + nb && c + 1 <= r) v1 = A[(size_t)r * p + c + 1] - s1;
+                if (r <= p) {
+                    const double* Ar = r < p ? A + (size_t)r * p : x;
+                    if (c < kb + nb && c <= r) v0 = Ar[c] - s0;
+                    if (c + 1 < kb + nb && c + 1 <= r) v1 = Ar[c + 1] - s1;
                 }
                 *reinterpret_cast<double2*>(P + (size_t)rr * kPPitch + cp) = make_double2(v0, v1);
             }
@@ -237,7 +242,8 @@ __device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, d
         }
         // (3) panel rows below the diagonal block:  X = U L11^-T = U M'  — one more 32-wide GEMM on DMMA per 32-row block
         //     (A fragments from P, B[k][n] = M[n][k] from W), straight to global memory
-        for (int b = 1 + warp; b < nrb; b += nwarps) {
+        //     (the last, ragged panel keeps the rhs row inside block 0, right under the nb rows of the diagonal block)
+        for (int b = (nb < kNB ? 0 : 1) + warp; b < nrb; b += nwarps) {
             double c0[4][4], c1[4][4];
 #pragma unroll
             for (int ti = 0; ti < 4; ti++)
@@ -261,10 +267,14 @@ __device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, d
 #pragma unroll
             for (int ti = 0; ti < 4; ti++) {
                 const int r = kb + 32 * b + 8 * ti + a8;
-                if (r < p) {
+                if (r <= p && r >= kb + nb) {
 #pragma unroll
-                    for (int tj = 0; tj < 4; tj++)
-                        *reinterpret_cast<double2*>(L + (size_t)r * ld + kb + 8 * tj + 2 * q) = make_double2(c0[ti][tj], c1[ti][tj]);
+                    for (int tj = 0; tj < 4; tj++) {
+                        const int c = 8 * tj + 2 * q;   // a ragged panel has nb < 32 columns: nothing past them (row p is
+                        double* dst = L + (size_t)r * ld + kb + c;   // the LAST row of this matrix's workspace)
+                        if (c + 1 < nb) *reinterpret_cast<double2*>(dst) = make_double2(c0[ti][tj], c1[ti][tj]);
+                        else if (c < nb) *dst = c0[ti][tj];
+                    }
                 }
             }
         }
@@ -272,38 +282,15 @@ __device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, d
     }
 }
 
-// x = (L L')^-1 x with the factor in global memory: blocked forward and backward substitution (diagonal block solved by
-// warp 0 with the lane's row / column of the block in registers, the rest of x updated by all threads)
+// x = (L L')^-1 b with the factor in global memory: z = L^-1 b is row p of the factor (see above); blocked backward
+// substitution (diagonal block solved by warp 0 with the lane's column of the block in registers, the rest of x updated by
+// all threads)
 __device__ __forceinline__ void chol_blocked_solve_cta(const double* L, int ld, int p, double* x) {
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
     __syncthreads();  // the last diagonal block was written back by all threads
-    for (int kb = 0; kb < p; kb += kNB) {  // forward: L z = b
-        const int nb = (p - kb < kNB) ? (p - kb) : kNB;
-        if (warp == 0) {
-            double lrow[kNB];
-#pragma unroll
-            for (int j = 0; j < kNB; j++) lrow[j] = (lane < nb && j <= lane) ? L[(size_t)(kb + lane) * ld + kb + j] : 1.0;
-            double xr = (lane < nb) ? x[kb + lane] : 0.0;
-            double rinv = 1.0;   // 1 / L[lane][lane]: one division per lane up front instead of one per step of the chain
-#pragma unroll
-            for (int j = 0; j < kNB; j++) rinv = (lane == j) ? 1.0 / lrow[j] : rinv;
-#pragma unroll
-            for (int j = 0; j < kNB; j++) {
-                const double xj = __shfl_sync(0xffffffffu, xr * rinv, j);
-                if (lane == j) xr = xj;
-                if (lane > j) xr = fma(-lrow[j], xj, xr);
-            }
-            if (lane < nb) x[kb + lane] = xr;
-        }
-        __syncthreads();
-        for (int i = kb + nb + tid; i < p; i += nt) {
-            const double* row = L + (size_t)i * ld + kb;
-            double sacc = 0.0;
-            for (int t = 0; t < nb; t++) sacc = fma(row[t], x[kb + t], sacc);
-            x[i] -= sacc;
-        }
-        __syncthreads();
-    }
+    // forward substitution: done by the factorisation (row p of L is z = L^-1 b)
+    for (int i = tid; i < p; i += nt) x[i] = L[(size_t)p * ld + i];
+    __syncthreads();
     const int nblk = (p + kNB - 1) / kNB;
     for (int bi = nblk - 1; bi >= 0; bi--) {  // backward: L' x = z
         const int kb = bi * kNB;
@@ -354,7 +341,7 @@ __global__ void __launch_bounds__(SMEM ? kCholThreads : kCholThreadsBlocked) cho
         ld = p | 1;  // odd leading dimension: column walks hit distinct banks
     } else {
         ld = (p + 1) & ~1;  // even: every row of the factor starts 16-byte aligned (two doubles per fragment load)
-        L = gws + (size_t)k * p * ld;
+        L = gws + (size_t)k * (p + 1) * ld;
     }
     const double* Ak = A + (size_t)k * p * p;
     if (SMEM) {
@@ -421,7 +408,7 @@ __global__ void __launch_bounds__(SMEM ? kCholThreads : kCholThreadsBlocked) cho
 static size_t chol_smem_bytes(int p) { return ((size_t)((p + 1) & ~1) + (size_t)p * (p | 1)) * sizeof(double); }
 
 size_t chol_workspace_bytes(int K, int p) {
-    return p <= kCholSmemMaxP ? 0 : (size_t)K * p * ((p + 1) & ~1) * sizeof(double);
+    return p <= kCholSmemMaxP ? 0 : (size_t)K * (p + 1) * ((p + 1) & ~1) * sizeof(double);   // p + 1 rows: the rhs row
 }
 
 int chol_launch(const double* A, const double* b, int K, int p, int mode, double* beta, double* x_out,
@@ -437,7 +424,7 @@ int chol_launch(const double* A, const double* b, int K, int p, int mode, double
         const size_t need = chol_workspace_bytes(K, p);
         DLSA_REQUIRE(workspace != nullptr && workspace_bytes >= need, DLSA_E_WORKSPACE,
                      "cholesky: workspace too small (%zu < %zu)", workspace_bytes, need);
-        const int prow = (p + 31) & ~31;   // the panel holds every row from the diagonal block down, in 32-row blocks
+        const int prow = (p + 32) & ~31;   // the panel holds every row from the diagonal block down to the rhs row, in 32-row blocks
         const size_t smem = ((size_t)((p + 1) & ~1) + (size_t)kNB * kDPitch + kNB + (size_t)kNB * kPPitch +
                              (size_t)prow * kPPitch) * sizeof(double);
         DLSA_CUDA(cudaFuncSetAttribute(chol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
