@@ -204,29 +204,34 @@ __device__ __forceinline__ void chol_blocked_cta(const double* __restrict__ A, d
                 const double rs = rsqrt(d);                          // one reciprocal square root instead of sqrt + divide on the
                 const double lj = row[j] * rs;                       // 32-step dependent chain: column j of the factor (lane j: d/sqrt(d))
                 row[j] = lj;
+                // column j goes round through shared memory (W is free until the inverse is formed; two buffers, so a
+                // fast lane's next column cannot overwrite what a slow lane still reads): one broadcast load per element
+                // instead of two shuffles
+                double* colbuf = W + (j & 1) * kNB;
+                colbuf[lane] = lj;
+                __syncwarp();
 #pragma unroll
-                for (int c = j + 1; c < kNB; c++) {
-                    const double lc = __shfl_sync(0xffffffffu, lj, c);
-                    row[c] = fma(-lj, lc, row[c]);   // only c <= lane is ever read; the rest is harmless garbage
-                }
+                for (int c = j + 1; c < kNB; c++) row[c] = fma(-lj, colbuf[c], row[c]);   // only c <= lane is ever read
             }
             if (good) {
 #pragma unroll
                 for (int c = 0; c < kNB; c++) D[lane * kDPitch + c] = row[c];
                 // M = L11^-1 (lower triangular), lane j owns column j in registers:
-                //   M[i][j] = -(sum_{t=j}^{i-1} L11[i][t] M[t][j]) / L11[i][i];  L11[i][t] comes from lane i by shuffle
+                //   M[i][j] = -(sum_{t=j}^{i-1} L11[i][t] M[t][j]) / L11[i][i];  L11[i][t] is read back from D (one broadcast
+                //   load instead of two shuffles, and the lane's row of the factor need not stay in registers next to m[])
                 double m[kNB];
                 const double dinv = 1.0 / row[lane];
                 invd[lane] = dinv;
+                __syncwarp();
 #pragma unroll
                 for (int i = 0; i < kNB; i++) {
                     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                     for (int t = 0; t < i; t++) {
-                        const double lit = __shfl_sync(0xffffffffu, row[t], i);
+                        const double lit = D[i * kDPitch + t];
                         if (t & 1) s1 = fma(lit, m[t], s1); else s0 = fma(lit, m[t], s0);
                     }
-                    const double di = __shfl_sync(0xffffffffu, dinv, i);
+                    const double di = invd[i];
                     m[i] = (lane == i) ? dinv : ((lane < i) ? -(s0 + s1) * di : 0.0);
                     W[i * kPPitch + lane] = m[i];
                 }
