@@ -247,3 +247,26 @@ def test_categorical_plan_gives_every_level_one_home():
     bad = (C.c_int * 9)(*([3] * 9))
     assert _lib.lib.dlsa_irls_cat_plan(4, 8, 2, bad, 100, info, cat, tile) != 0    # 8 numeric columns
     assert _lib.lib.dlsa_irls_cat_plan(4, 2, 9, bad, 100, info, cat, tile) != 0    # 9 categorical columns
+
+
+def test_tiled_slices_follow_the_cost_model():
+    """Slices per partition of the tiled pass, read back from the workspace size (K * S partial H buffers, none for
+    S = 1): short partitions in a launch that already fills the SMs are NOT sliced (the wave-fill rule of round 1 cut the
+    2500-row partitions of C5 five ways); few long partitions are sliced to fill the machine."""
+    from dlsa_b200 import _lib
+    lib = _lib.lib
+
+    def slices(K, p, rows):
+        b = lib.dlsa_irls_pass_workspace_bytes(K, p, rows)
+        per, pre = (p * p + p + 1) * 8, 3 * K * rows * 8
+        for S in range(1, 33):
+            base = 0 if S == 1 else K * S * per
+            if b in (base, base + pre):
+                return S
+        raise AssertionError((K, p, rows, b))
+
+    assert slices(1024, 500, 2500) == 1 and slices(8192, 500, 2500) == 1 and slices(1024, 100, 2500) == 1
+    assert slices(15, 182, 1_000_000) >= 8          # 15 partitions x 3 sibling CTAs cannot fill 148 SMs
+    assert slices(32, 100, 976_563) >= 4 and slices(1, 100, 1_000_000) == 32
+    for K, p, rows in [(3, 64, 100), (7, 300, 40), (148, 200, 5000)]:
+        assert 1 <= slices(K, p, rows) <= 32
