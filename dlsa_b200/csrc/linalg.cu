@@ -411,6 +411,139 @@ __global__ void __launch_bounds__(SMEM ? kCholThreads : kCholThreadsBlocked) cho
     }
 }
 
+// ---- p <= 64: ONE WARP per matrix ------------------------------------------------------------------------------------
+// The CTA version above spends its time in block-wide barriers (3 per column, 2 per substitution step: ~110 us for the
+// 1024 50x50 systems of C2).  Here a warp owns one system in its own slice of shared
+// memory (odd row pitch: a lane per row walks distinct banks) and only ever needs __syncwarp:
+//   * left-looking factorisation, column j: lane r takes rows j + r, j + r + 32 (and j + r + 64): the dot products over the
+//     finished columns read the lane's own row and broadcast row j;
+//   * the right-hand side is row p of the matrix, so its factor row is z = L^-1 b (as in the blocked kernel);
+//   * back substitution with z in registers (lane owns entries lane and lane + 32), x_j broadcast by shuffle, and the
+//     reciprocal diagonal kept from the factorisation: no division on the chain.
+constexpr int kCholWarpMaxP = 64;
+
+static int chol_warp_per_cta(int p) {
+    const size_t per_warp = ((size_t)(p + 1) * (p | 1) + kCholWarpMaxP) * sizeof(double);
+    int w = (int)((size_t)(200 * 1024) / per_warp);
+    return w > 8 ? 8 : (w < 1 ? 1 : w);
+}
+
+__global__ void __launch_bounds__(256) chol_warp_kernel(const double* __restrict__ A, const double* __restrict__ b, int K, int p,
+                                                        int mode, double* beta, double* x_out, double* max_delta, int* status,
+                                                        int* active, int* iters, int* n_active, double tol, double damp_above,
+                                                        double damp_factor) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (k >= K) return;   // no block-wide barrier below
+    if (mode == 0 && active != nullptr && active[k] == 0) return;
+    const int ld = p | 1;
+    double* L = reinterpret_cast<double*>(smem_raw) + (size_t)warp * ((size_t)(p + 1) * ld + kCholWarpMaxP);
+    double* dinv = L + (size_t)(p + 1) * ld;
+    const double* Ak = A + (size_t)k * p * p;
+    // the whole p x p block in batches of 16 coalesced loads per lane, all in flight before the first store (a row-by-row
+    // copy of the lower triangle serialises p global-memory latencies: 83 us per call instead of 2x this kernel's arithmetic)
+    const int n2 = p * p;
+    for (int e0 = 0; e0 < n2; e0 += 32 * 16) {
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int e = e0 + lane + 32 * q;
+            v[q] = (e < n2) ? __ldg(Ak + e) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int e = e0 + lane + 32 * q;
+            if (e < n2) {
+                const int i = e / p, c = e - i * p;
+                if (c <= i) L[i * ld + c] = v[q];
+            }
+        }
+    }
+    for (int c = lane; c < p; c += 32) L[p * ld + c] = b[(size_t)k * p + c];
+    __syncwarp();
+    bool good = true;
+    for (int j = 0; j < p; j++) {
+        const double* Lj = L + j * ld;
+        const int i0 = j + lane, i1 = i0 + 32, i2 = i0 + 64;
+        const bool ok0 = i0 <= p, ok1 = i1 <= p, ok2 = i2 <= p;
+        const double* R0 = L + (ok0 ? i0 : j) * ld;
+        const double* R1 = L + (ok1 ? i1 : j) * ld;
+        const double* R2 = L + (ok2 ? i2 : j) * ld;
+        double a0 = R0[j], a1 = R1[j], a2 = R2[j];
+        if (j + 64 <= p) {   // warp-uniform: a third row per lane only while more than 64 rows are left (p = 64, j = 0)
+            for (int t = 0; t < j; t++) {
+                const double ljt = Lj[t];
+                a0 = fma(-R0[t], ljt, a0);
+                a1 = fma(-R1[t], ljt, a1);
+                a2 = fma(-R2[t], ljt, a2);
+            }
+        } else {
+            for (int t = 0; t < j; t++) {   // (four columns per trip with split partial sums: no faster, 0.066 ms either way)
+                const double ljt = Lj[t];
+                a0 = fma(-R0[t], ljt, a0);
+                a1 = fma(-R1[t], ljt, a1);
+            }
+        }
+        const double d = __shfl_sync(0xffffffffu, a0, 0);   // lane 0 holds row j: the pivot
+        good = good && (d > 0.0) && isfinite(d);
+        const double rs = rsqrt(d);
+        __syncwarp();   // every lane has read row j before lane 0 rewrites its entry (j, j)
+        if (ok0) L[i0 * ld + j] = a0 * rs;
+        if (ok1) L[i1 * ld + j] = a1 * rs;
+        if (ok2) L[i2 * ld + j] = a2 * rs;
+        if (lane == 0) dinv[j] = rs;
+        __syncwarp();
+    }
+    // z = row p of the factor; x = L^-T z, entries lane and lane + 32 in registers
+    double z0 = (lane < p) ? L[p * ld + lane] : 0.0;
+    double z1 = (lane + 32 < p) ? L[p * ld + lane + 32] : 0.0;
+    for (int j = p - 1; j >= 0; j--) {
+        const double zj = __shfl_sync(0xffffffffu, (j < 32) ? z0 : z1, j & 31);
+        const double xj = zj * dinv[j];
+        if (lane == (j & 31)) { if (j < 32) z0 = xj; else z1 = xj; }
+        const double* Lj = L + j * ld;
+        if (lane < j) z0 = fma(-Lj[lane], xj, z0);
+        if (lane + 32 < j) z1 = fma(-Lj[lane + 32], xj, z1);
+    }
+    const bool ok = good;
+    if (mode == 1) {
+        if (lane < p) x_out[(size_t)k * p + lane] = ok ? z0 : 0.0;
+        if (lane + 32 < p) x_out[(size_t)k * p + lane + 32] = ok ? z1 : 0.0;
+        if (lane == 0 && status != nullptr) status[k] = ok ? DLSA_ST_OK : DLSA_ST_NOT_SPD;
+        return;
+    }
+    // Newton bookkeeping (same rules as chol_kernel)
+    double md = fmax((lane < p) ? fabs(z0) : 0.0, (lane + 32 < p) ? fabs(z1) : 0.0);
+    bool finite = isfinite(md);
+    if (!finite) md = INFINITY;
+    for (int m = 16; m >= 1; m >>= 1) md = fmax(md, __shfl_xor_sync(0xffffffffu, md, m));
+    if (!ok || !isfinite(md)) {
+        if (lane == 0) {
+            status[k] = DLSA_ST_NOT_SPD;
+            active[k] = 0;
+            if (max_delta) max_delta[k] = INFINITY;
+        }
+        return;
+    }
+    const double scale = (md > damp_above) ? damp_factor : 1.0;  // dlsa/R/wlse_func.R:56-60
+    if (md > tol) {   // a sub-tolerance step is not applied (see chol_kernel)
+        if (lane < p) beta[(size_t)k * p + lane] += scale * z0;
+        if (lane + 32 < p) beta[(size_t)k * p + lane + 32] += scale * z1;
+    }
+    if (lane == 0) {
+        if (max_delta) max_delta[k] = md;
+        iters[k] += 1;
+        if (md <= tol) {
+            active[k] = 0;
+            status[k] = DLSA_ST_OK;
+        } else {
+            status[k] = DLSA_ST_NOT_CONVERGED;
+            atomicAdd(n_active, 1);
+        }
+    }
+}
+
 static size_t chol_smem_bytes(int p) { return ((size_t)((p + 1) & ~1) + (size_t)p * (p | 1)) * sizeof(double); }
 
 size_t chol_workspace_bytes(int K, int p) {
@@ -421,7 +554,13 @@ int chol_launch(const double* A, const double* b, int K, int p, int mode, double
                 double* max_delta, int* status, int* active, int* iters, int* n_active, double tol, double damp_above,
                 double damp_factor, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (K == 0) return 0;
-    if (p <= kCholSmemMaxP) {
+    if (p <= kCholWarpMaxP) {
+        const int wpc = chol_warp_per_cta(p);
+        const size_t smem = (size_t)wpc * ((size_t)(p + 1) * (p | 1) + kCholWarpMaxP) * sizeof(double);
+        DLSA_CUDA(cudaFuncSetAttribute(chol_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chol_warp_kernel<<<(K + wpc - 1) / wpc, wpc * 32, smem, st>>>(A, b, K, p, mode, beta, x_out, max_delta, status, active,
+                                                                      iters, n_active, tol, damp_above, damp_factor);
+    } else if (p <= kCholSmemMaxP) {
         const size_t smem = chol_smem_bytes(p);
         DLSA_CUDA(cudaFuncSetAttribute(chol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         chol_kernel<true><<<K, kCholThreads, smem, st>>>(A, b, K, p, mode, beta, x_out, max_delta, status, active, iters,

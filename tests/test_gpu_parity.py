@@ -612,7 +612,7 @@ def test_poisson_dlsa_end_to_end(eng):
     assert np.array_equal(path.beta[path.argmin_BIC].cpu().numpy() != 0, truth != 0)
 
 
-@pytest.mark.parametrize("p", [1, 7, 50, 160, 161, 192, 200, 333, 500, 512])
+@pytest.mark.parametrize("p", [1, 2, 7, 32, 33, 50, 63, 64, 65, 160, 161, 192, 200, 333, 500, 512])
 def test_batched_spd_solve_matches_lapack(eng, p):
     """K5 / the solve inside K2 (np.linalg.lstsq(Sig_inv_sum, ...) of dlsa/dlsa.py:48; solve(hess) of
     dlsa/R/wlse_func.R:55): shared-memory factorisation up to p = 160, blocked DMMA factorisation of the global-memory
